@@ -358,22 +358,26 @@ class RefRadex:
         self.dview("ctot", MAXLEV)[:nlev] = ctot
         self.set_scalar("totdens", totdens)
 
-    def run_pyradex_loop(self, reuse_last=False, miniter=10, maxiter=200, abs_tol=1e-16, trace=None):
+    def run_pyradex_loop(self, reuse_last=False, miniter=10, maxiter=200, abs_tol=1e-16, rel_tol=1e-8, trace=None):
         """The python loop of emcee/pyradex/core.py:896-925 around the binary's matrix()."""
-        nlev = self.get_int("nlev")
+        # level_population is the full 2999-long COMMON array in pyradex; the sums below run over
+        # all of it (numpy pairwise summation), which fixes the rounding of the 1e-16 stop test.
         xpop = self.dview("xpop", MAXLEV)
+        nlev = self.get_int("nlev")
         it = 1 if reuse_last else 0
-        last = xpop[:nlev].copy()
+        last = xpop.copy()
         while True:
             if it >= maxiter:
                 break
             self.matrix(it)
             if trace is not None:
                 trace.append(xpop[:nlev].copy())
-            diff = np.abs(last - xpop[:nlev]).sum()
-            if diff < abs_tol and it > miniter:
+            level_diff = np.abs(last - xpop)
+            with np.errstate(all="ignore"):
+                frac_level_diff = level_diff / xpop
+            if ((level_diff.sum() < abs_tol) or (frac_level_diff.sum() < rel_tol)) and it > miniter:
                 break
-            last = xpop[:nlev].copy()
+            last = xpop.copy()
             it += 1
         return it
 

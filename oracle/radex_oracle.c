@@ -278,7 +278,7 @@ void ro_backrad(ro_state *s, double tbg) {
     double hnu = RO_FK * m->xnu[l] / tbg;
     double v;
     if (hnu >= 160.0) v = 1.0e-30;   /* eps */
-    else v = RO_THC * (m->xnu[l] * m->xnu[l] * m->xnu[l]) / (exp(hnu) - 1.0);
+    else v = RO_THC * pow(m->xnu[l], 3.0) / (exp(hnu) - 1.0);   /* xnu**3. compiles to pow() */
     s->backi[l] = v;
     s->totalb[l] = v;
     s->trj[l] = tbg;
@@ -365,7 +365,7 @@ int ro_matrix(ro_state *s, int niter) {
   const int nl = m->nlev, nn = m->nline, np = nl + 1;
   double *y = s->yrate;              /* column-major y[i + j*np] == yrate(i+1, j+1) */
   double *rhs = s->rhs;
-  const double eps_td = RO_F(1.0e-30) * s->totdens;
+  const double eps_td = 1.0e-30 * s->totdens;   /* 1.0d-30 literal: verified bitwise against the binary yrate */
   int conv = 0;
 #define Y(i, j) y[(i) + (size_t)(j) * np]
   for (int i = 0; i < nl; ++i) {
@@ -384,7 +384,7 @@ int ro_matrix(ro_state *s, int niter) {
       double exr = (etr >= 160.0) ? 0.0 : 1.0 / (exp(etr) - 1.0);
       double a = m->aeinst[l], gm = m->gstat[mu], gn = m->gstat[n];
       Y(mu, mu) += a * (1.0 + exr);
-      Y(n, n) += a * (gm * exr / gn);
+      Y(n, n) += a * gm * exr / gn;      /* niter=0 branch has no parentheses: ((a*gm)*exr)/gn */
       Y(mu, n) -= a * (gm / gn) * exr;
       Y(n, mu) -= a * (1.0 + exr);
     }
@@ -394,7 +394,7 @@ int ro_matrix(ro_state *s, int niter) {
     s->nfat = 0;
     for (int l = 0; l < nn; ++l) {
       int mu = m->iupp[l] - 1, n = m->ilow[l] - 1;
-      double xt = m->xnu[l] * m->xnu[l] * m->xnu[l];
+      double xt = pow(m->xnu[l], 3.0);
       double a = m->aeinst[l], gm = m->gstat[mu], gn = m->gstat[n];
       s->taul[l] = cddv * (s->xpop[n] * gm / gn - s->xpop[mu]) / (/*fgaus*/ RO_F(1.0645) * 8.0 * RO_PI * xt / a);
       if (s->taul[l] > 1.0e-2) s->nthick++;
@@ -441,7 +441,7 @@ int ro_matrix(ro_state *s, int niter) {
   double tsum = 0.0;
   for (int l = 0; l < nn; ++l) {
     int mu = m->iupp[l] - 1, n = m->ilow[l] - 1;
-    double xt = m->xnu[l] * m->xnu[l] * m->xnu[l];
+    double xt = pow(m->xnu[l], 3.0);
     double gm = m->gstat[mu], gn = m->gstat[n];
     if (niter == 0) {
       if (s->xpop[n] <= RO_MINPOP || s->xpop[mu] <= RO_MINPOP) s->tex[l] = s->totalb[l];
@@ -471,16 +471,42 @@ enum { RO_STOP_PYRADEX = 0, RO_STOP_RADEX = 1 };
  * and continues from whatever state holds.  stop_rule RO_STOP_PYRADEX = the loop as written
  * (sum|dx| < abs_tol and iter > miniter; the relative test is NaN-dead);
  * RO_STOP_RADEX = Fortran's own conv flag.  Returns _iter_counter.                             */
+/* numpy's pairwise summation (DOUBLE_pairwise_sum), which is what `level_diff.sum()` runs over the
+ * 2999-long, zero-padded level_population array (core.py:911-914).                              */
+static double ro_np_pairwise(const double *a, long n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (long i = 0; i < n; ++i) res += a[i];
+    return res;
+  } else if (n <= 128) {
+    double r[8];
+    long i;
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    for (i = 8; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+  } else {
+    long n2 = n / 2;
+    n2 -= n2 % 8;
+    return ro_np_pairwise(a, n2) + ro_np_pairwise(a + n2, n - n2);
+  }
+}
+
+#define RO_PYRADEX_MAXLEV 2999   /* length of collie.xpop in this build */
+
 int ro_run(ro_state *s, int reuse_last, int stop_rule, int miniter, int maxiter, double abs_tol) {
   int nl = s->mol->nlev;
   int it = reuse_last ? 1 : 0;
-  double last[4096];
+  static __thread double last[RO_PYRADEX_MAXLEV], diff[RO_PYRADEX_MAXLEV];
+  memset(diff, 0, sizeof(diff));
   memcpy(last, s->xpop, sizeof(double) * nl);
   for (;;) {
     if (it >= maxiter) break;
     int conv = ro_matrix(s, it);
-    double d = 0.0;
-    for (int i = 0; i < nl; ++i) d += fabs(last[i] - s->xpop[i]);
+    for (int i = 0; i < nl; ++i) diff[i] = fabs(last[i] - s->xpop[i]);
+    double d = ro_np_pairwise(diff, RO_PYRADEX_MAXLEV);
     if (stop_rule == RO_STOP_RADEX) {
       if (conv) break;
     } else if (d < abs_tol && it > miniter) {
@@ -649,3 +675,7 @@ void ro_solve_batch(ro_state *s, long n, const double *tkin, const double *n_ph2
     if (surf) memcpy(surf + i * nn, sb, sizeof(double) * nn);
   }
 }
+
+/* debugging/validation accessor: the assembled (nlev+1)^2 rate matrix of the last ro_matrix call
+ * is destroyed only in the reduced copy, so yrate can be compared with the binary's yrate.     */
+double *ro_state_yrate(ro_state *s) { return s->yrate; }

@@ -1,0 +1,1134 @@
+// libradex_b200 -- CUDA kernels (sm_100a) and C ABI for the RADEX escape-probability hot path.
+//
+// Reference path being replaced (all relative to /root/reference):
+//   emcee/emcee_radex.py:120-181, emcee/emcee_radex_2comp.py:122-244   lnprob / lnprior / lnlike / model_lvg
+//   emcee/pyradex/core.py:388-438, 856-925, 986-1003                   set_params / run_radex / brightness
+//   emcee/pyradex/radex/radex.so  readdata@0x1cf90 backrad@0x1be30 matrix@0x17f70 escprob@0xa9c0
+//                                 lubksb@0x17cb0 -> sgeir@0x16d50 -> sgefa@0xf3d0 / sgesl@0xdb70
+//
+// One warp owns one model (walker component) from parameter load to line fluxes; nothing but the
+// walker parameters and the requested outputs ever touches HBM.  See DESIGN.md for the layout.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// constants: exactly the values in the reference binary's constant pool
+// ------------------------------------------------------------------------------------------------
+#define RB_FK 1.4387809925261357        // h c / k  (radex.inc)
+#define RB_THC 3.972907393443411e-16    // 2 h c    (radex.inc)
+#define RB_PI_TRUNC 3.14159265          // radex.inc's pi
+#define RB_MINPOP 1.0e-20
+#define RB_F32(x) ((double)(x##f))      // single-precision Fortran literal promoted to double
+#define RB_FGAUS (RB_F32(1.0645) * 8.0 * RB_PI_TRUNC)
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      rb_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                         \
+      return RB_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device-resident molecular table (SoA); passed to kernels by value
+// ------------------------------------------------------------------------------------------------
+struct MolDev {
+  int nlev, nline, npart;
+  const double *eterm, *gstat;            // [nlev]
+  const int *iupp, *ilow;                 // [nline] 0-based
+  const double *aeinst, *xnu;             // [nline]
+  const int *lev_ptr;                     // [nlev+1] CSR: lines incident on each level, in line order
+  const int *lev_line;                    // [2*nline] line index, bit 30 set when the level is the upper one
+  int part_id[RB_MAXPART], ntemp[RB_MAXPART], ncoll[RB_MAXPART];
+  const double *temps[RB_MAXPART];        // [ntemp]
+  const int *lcu[RB_MAXPART], *lcl[RB_MAXPART];  // [ncoll] 0-based
+  const double *rates_tc[RB_MAXPART];     // [ntemp][ncoll]
+};
+
+struct SolveCfg {
+  double deltav_cms, tbg;
+  int method, stop_rule, miniter, maxiter;
+  double abs_tol, fk_epi, thc_epi;
+};
+
+struct rb_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  MolDev mol{};
+  std::vector<void *> owned;              // device allocations of the tables
+  // grow-only scratch for the host-pointer entry points
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  unsigned long long *counters = nullptr; // [0] work queue head, [1] total iterations, [2] solves
+  long long launches = 0;
+  long long last_total_iters = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// escape probability, three geometries (radex.so@0xa9c0; oracle/radex_oracle.c ro_escprob)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rb_escprob(double tau, int method) {
+  const double taur = tau * 0.5;
+  double beta;
+  if (method == RB_GEOM_LVG) {
+    const double at = fabs(taur);
+    if (at < RB_F32(0.01)) {
+      beta = 1.0;
+    } else if (at < 7.0) {
+      beta = 2.0 * (1.0 - exp(-RB_F32(2.34) * taur)) / (RB_F32(4.68) * taur);
+    } else {
+      beta = 2.0 / (taur * 4.0 * sqrt(log(taur / sqrt(RB_PI_TRUNC))));
+    }
+  } else if (method == RB_GEOM_SPHERE) {
+    const double at = fabs(taur);
+    if (at < RB_F32(0.1)) {
+      beta = 1.0 - 0.75 * taur + (taur * taur) / 2.5 - (taur * taur * taur) / 6.0 +
+             (taur * taur * taur * taur) / 17.5;
+    } else if (at > 50.0) {
+      beta = 0.75 / taur;
+    } else {
+      beta = 0.75 / taur *
+             (1.0 - 1.0 / (2.0 * (taur * taur)) + (1.0 / taur + 1.0 / (2.0 * (taur * taur))) * exp(-2.0 * taur));
+    }
+  } else {
+    const double t3 = fabs(3.0 * tau);
+    if (t3 < RB_F32(0.1)) {
+      beta = 1.0 - 1.5 * (tau + tau * tau);
+    } else if (t3 > 50.0) {
+      beta = 1.0 / (3.0 * tau);
+    } else {
+      beta = (1.0 - exp(-3.0 * tau)) / (3.0 * tau);
+    }
+  }
+  return beta;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// v1 solver: one warp per model, rate matrix in shared memory, partial-pivot LU exactly as the
+// reference build does it (reduced nlev x nlev system, last equation replaced by conservation).
+// ------------------------------------------------------------------------------------------------
+struct WarpMem {             // carved out of dynamic shared memory, one per warp
+  double *A;                 // [nlev*nlev] column-major work matrix (also holds crate[i*nlev+j] in the prologue)
+  double *B;                 // [nlev*nlev] column-major collisional part incl. -eps (constant over iterations)
+  double *ctot, *xpop, *xold, *rhs;  // [nlev]
+  double *tex, *taul, *backi, *dn, *up, *upx;  // [nline]
+};
+
+__host__ __device__ inline size_t v1_warp_doubles(int nlev, int nline) {
+  return (size_t)2 * nlev * nlev + 4 * (size_t)nlev + 6 * (size_t)nline;
+}
+
+__device__ __forceinline__ WarpMem carve(double *base, int nlev, int nline) {
+  WarpMem w;
+  w.A = base;
+  w.B = w.A + nlev * nlev;
+  w.ctot = w.B + nlev * nlev;
+  w.xpop = w.ctot + nlev;
+  w.xold = w.xpop + nlev;
+  w.rhs = w.xold + nlev;
+  w.tex = w.rhs + nlev;
+  w.taul = w.tex + nline;
+  w.backi = w.taul + nline;
+  w.dn = w.backi + nline;
+  w.up = w.dn + nline;
+  w.upx = w.up + nline;
+  return w;
+}
+
+// collision rates at tkin: clamped linear interpolation, partner mix, detailed balance, ctot
+// (readdata, radex.so@0x1cf90; oracle ro_set_physics).  Result: crate in w.A (row-major
+// crate[i*nlev+j] = rate i->j), ctot in w.ctot, returns totdens.
+__device__ double v1_rates(const MolDev &mol, const WarpMem &w, int lane, double tkin, const double *dens) {
+  const int nl = mol.nlev;
+  for (int e = lane; e < nl * nl; e += 32) w.A[e] = 0.0;
+  __syncwarp();
+  double totdens = 0.0;
+  for (int p = 0; p < mol.npart; ++p) {
+    const double d = dens[p];
+    totdens += d;
+    const double *T = mol.temps[p];
+    const int nt = mol.ntemp[p];
+    int t0 = 0;
+    double fint = 0.0;
+    int mode;  // 0 low clamp, 1 high clamp, 2 interpolate
+    if (tkin <= T[0]) {
+      mode = 0;
+    } else if (tkin >= T[nt - 1]) {
+      mode = 1;
+    } else {
+      mode = 2;
+      for (int t = 0; t < nt - 1; ++t)
+        if (tkin > T[t] && tkin <= T[t + 1]) {
+          t0 = t;
+          fint = (tkin - T[t]) / (T[t + 1] - T[t]);
+          break;
+        }
+    }
+    const double *R = mol.rates_tc[p];
+    const int nc = mol.ncoll[p];
+    for (int c = lane; c < nc; c += 32) {
+      double v;
+      if (mode == 0) {
+        v = __ldg(R + c);
+      } else if (mode == 1) {
+        v = __ldg(R + (size_t)(nt - 1) * nc + c);
+      } else {
+        const double r0 = __ldg(R + (size_t)t0 * nc + c), r1 = __ldg(R + (size_t)(t0 + 1) * nc + c);
+        v = r0 + fint * (r1 - r0);
+        if (v < 0.0) v = r0;
+      }
+      const int iu = mol.lcu[p][c], il = mol.lcl[p][c];
+      w.A[iu * nl + il] += d * v;
+    }
+    __syncwarp();
+  }
+  for (int e = lane; e < nl * nl; e += 32) {
+    const int iu = e / nl, il = e - iu * nl;
+    const double ediff = mol.eterm[iu] - mol.eterm[il];
+    if (ediff > 0.0) {
+      const double x = RB_FK * ediff / tkin;
+      w.A[il * nl + iu] = (x >= 160.0) ? 0.0 : mol.gstat[iu] / mol.gstat[il] * exp(-x) * w.A[iu * nl + il];
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < nl; i += 32) {
+    double t = 0.0;
+    for (int j = 0; j < nl; ++j) t += w.A[i * nl + j];
+    w.ctot[i] = t;
+  }
+  __syncwarp();
+  return totdens;
+}
+
+// LU with partial pivoting + solve on the nl x nl column-major matrix in w.A, rhs in w.rhs
+// (sgefa/sgesl; oracle ro_gefa/ro_gesl).  Lanes run down the rows of a column.
+__device__ void v1_lu_solve(const WarpMem &w, int nl, int lane) {
+  double *A = w.A;
+  double *b = w.rhs;
+  for (int k = 0; k < nl - 1; ++k) {
+    // pivot search: first index of max |A[i,k]|, i >= k
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + lane; i < nl; i += 32) {
+      const double v = fabs(A[i + k * nl]);
+      if (v > best) {
+        best = v;
+        bi = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    const int l = bi;
+    if (best == 0.0) continue;  // column already triangularised (sgefa's info path)
+    // row interchange across all columns k..nl-1 and in the rhs (sgesl applies it to b)
+    if (l != k) {
+      for (int j = k + lane; j < nl; j += 32) {
+        const double t = A[l + j * nl];
+        A[l + j * nl] = A[k + j * nl];
+        A[k + j * nl] = t;
+      }
+      if (lane == 0) {
+        const double t = b[l];
+        b[l] = b[k];
+        b[k] = t;
+      }
+      __syncwarp();
+    }
+    const double piv = A[k + k * nl];
+    const double t = -1.0 / piv;
+    // multipliers for my rows (kept in registers), two passes cover nl <= 64
+    const int i0 = k + 1 + lane, i1 = i0 + 32;
+    double m0 = 0.0, m1 = 0.0;
+    if (i0 < nl) {
+      m0 = A[i0 + k * nl] * t;
+      A[i0 + k * nl] = m0;
+    }
+    if (i1 < nl) {
+      m1 = A[i1 + k * nl] * t;
+      A[i1 + k * nl] = m1;
+    }
+    for (int j = k + 1; j < nl; ++j) {
+      const double tj = A[k + j * nl];
+      if (i0 < nl) A[i0 + j * nl] = fma(tj, m0, A[i0 + j * nl]);
+      if (i1 < nl) A[i1 + j * nl] = fma(tj, m1, A[i1 + j * nl]);
+    }
+    // forward elimination of the rhs with the same multipliers
+    const double bk = b[k];
+    if (i0 < nl) b[i0] = fma(bk, m0, b[i0]);
+    if (i1 < nl) b[i1] = fma(bk, m1, b[i1]);
+    __syncwarp();
+  }
+  for (int k = nl - 1; k >= 0; --k) {
+    const double xk = b[k] / A[k + k * nl];
+    __syncwarp();
+    if (lane == 0) b[k] = xk;
+    for (int i = lane; i < k; i += 32) b[i] = fma(-xk, A[i + k * nl], b[i]);
+    __syncwarp();
+  }
+}
+
+// One full solve.  On return w.xpop/tex/taul/backi hold the state pyradex would read back.
+// Returns the pyradex iteration counter; *status gets the rb_model_status bits.
+__device__ int v1_solve(const MolDev &mol, const WarpMem &w, int lane, double tkin, const double *dens, double cdmol,
+                        const SolveCfg &cfg, int *status) {
+  const int nl = mol.nlev, nn = mol.nline;
+  int st = 0;
+  if (!(tkin > 0.0 && tkin <= 1.0e4)) st |= RB_ST_T_RANGE;
+  if (!(cdmol >= 1.0e5 && cdmol <= 1.0e25)) st |= RB_ST_N_RANGE;
+  if (st) {
+    *status = st;
+    return 0;
+  }
+  const double totdens = v1_rates(mol, w, lane, tkin, dens);
+  const double eps_td = 1.0e-30 * totdens;
+  // constant part of the rate matrix, column-major: B(i,j) = -eps - crate(j,i); the diagonal is rebuilt
+  for (int e = lane; e < nl * nl; e += 32) {
+    const int j = e / nl, i = e - j * nl;
+    w.B[e] = (i == j) ? 0.0 : (-eps_td - w.A[j * nl + i]);
+  }
+  // background (backrad, tbg > 0 branch, radex.so@0x1be30): backi = totalb, trj = tbg
+  for (int l = lane; l < nn; l += 32) {
+    const double xnu = mol.xnu[l];
+    const double hnu = RB_FK * xnu / cfg.tbg;
+    w.backi[l] = (hnu >= 160.0) ? 1.0e-30 : RB_THC * (xnu * xnu * xnu) / (exp(hnu) - 1.0);
+    w.tex[l] = 0.0;
+    w.taul[l] = 0.0;
+  }
+  for (int i = lane; i < nl; i += 32) w.xpop[i] = 0.0;
+  __syncwarp();
+
+  const double cddv = cdmol / cfg.deltav_cms;
+  int it = 0;
+  int hit_max = 0;
+  for (;;) {
+    if (it >= cfg.maxiter) {
+      hit_max = 1;
+      break;
+    }
+    // ---- radiative rates per line ----------------------------------------------------------
+    int nthick = 0;
+    for (int l = lane; l < nn; l += 32) {
+      const int m = mol.iupp[l], n = mol.ilow[l];
+      const double a = mol.aeinst[l], gm = mol.gstat[m], gn = mol.gstat[n];
+      const double xnu = mol.xnu[l];
+      double beta, exr;
+      if (it == 0) {
+        const double etr = RB_FK * xnu / cfg.tbg;
+        exr = (etr >= 160.0) ? 0.0 : 1.0 / (exp(etr) - 1.0);
+        beta = 1.0;
+      } else {
+        const double xt = xnu * xnu * xnu;
+        const double tau = cddv * (w.xpop[n] * gm / gn - w.xpop[m]) / (RB_FGAUS * xt / a);
+        w.taul[l] = tau;
+        if (tau > 1.0e-2) ++nthick;
+        beta = rb_escprob(tau, cfg.method);
+        exr = w.backi[l] * beta / (RB_THC * xt);
+      }
+      w.dn[l] = a * (beta + exr);
+      w.up[l] = a * (gm * exr / gn);
+      w.upx[l] = a * (gm / gn) * exr;
+    }
+    nthick = warp_sum_int(nthick);
+    // ---- assemble: A = B, then diagonal and the line entries --------------------------------
+    for (int e = lane; e < nl * nl; e += 32) w.A[e] = w.B[e];
+    __syncwarp();
+    for (int i = lane; i < nl; i += 32) {
+      double s = -eps_td;
+      for (int q = mol.lev_ptr[i]; q < mol.lev_ptr[i + 1]; ++q) {
+        const int code = mol.lev_line[q];
+        const int l = code & 0x3fffffff;
+        s += (code & 0x40000000) ? w.dn[l] : w.up[l];
+      }
+      w.A[i + i * nl] = s + w.ctot[i];
+    }
+    for (int l = lane; l < nn; l += 32) {
+      const int m = mol.iupp[l], n = mol.ilow[l];
+      w.A[m + n * nl] -= w.upx[l];
+      w.A[n + m * nl] -= w.dn[l];
+    }
+    __syncwarp();
+    // reduced system of this build's lubksb: last equation := conservation, rhs = e_last
+    for (int j = lane; j < nl; j += 32) {
+      w.A[(nl - 1) + j * nl] = 1.0;
+      w.rhs[j] = (j == nl - 1) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    v1_lu_solve(w, nl, lane);
+    // ---- populations ------------------------------------------------------------------------
+    double part = 0.0;
+    for (int i = lane; i < nl; i += 32) part += w.rhs[i];
+    const double total = warp_sum(part);
+    for (int i = lane; i < nl; i += 32) {
+      double xo = fmax(RB_MINPOP, w.xpop[i]);
+      const double xn = fmax(RB_MINPOP, w.rhs[i] / total);
+      if (it == 0) xo = xn;
+      w.xold[i] = xo;
+      w.rhs[i] = xn;  // un-relaxed new populations
+    }
+    __syncwarp();
+    // ---- excitation temperatures, optical depths ----------------------------------------------
+    double tsum = 0.0;
+    for (int l = lane; l < nn; l += 32) {
+      const int m = mol.iupp[l], n = mol.ilow[l];
+      const double gm = mol.gstat[m], gn = mol.gstat[n];
+      const double xnu = mol.xnu[l];
+      const double xm = w.rhs[m], xn = w.rhs[n];
+      if (it == 0) {
+        w.tex[l] = (xn <= RB_MINPOP || xm <= RB_MINPOP) ? w.backi[l] : RB_FK * xnu / log(xn * gm / (xm * gn));
+      } else {
+        const double told = w.tex[l];
+        const double thistex =
+            (xn <= RB_MINPOP || xm <= RB_MINPOP) ? told : RB_FK * xnu / log(xn * gm / (xm * gn));
+        if (w.taul[l] > RB_F32(0.01)) tsum += fabs((thistex - told) / thistex);
+        w.tex[l] = 0.5 * (thistex + told);
+        w.taul[l] = cddv * (xn * gm / gn - xm) / (RB_FGAUS * (xnu * xnu * xnu) / mol.aeinst[l]);
+      }
+    }
+    tsum = warp_sum(tsum);
+    int conv = 0;
+    if (it >= 10) {  // miniter of radex.inc
+      if (nthick == 0) conv = 1;
+      else if (tsum / nthick < RB_F32(1.0e-6)) conv = 1;
+    }
+    // ---- under-relaxation + pyradex's stop test ------------------------------------------------
+    double diff = 0.0;
+    for (int i = lane; i < nl; i += 32) {
+      const double prev = w.xpop[i];
+      const double xr = RB_F32(0.3) * w.rhs[i] + RB_F32(0.7) * w.xold[i];
+      w.xpop[i] = xr;
+      diff += fabs(prev - xr);
+    }
+    diff = warp_sum(diff);
+    __syncwarp();
+    if (cfg.stop_rule == RB_STOP_RADEX) {
+      if (conv) break;
+    } else if (diff < cfg.abs_tol && it > cfg.miniter) {
+      break;
+    }
+    ++it;
+  }
+  if (hit_max) st |= RB_ST_MAXITER;
+  *status = st;
+  return it;
+}
+
+// source_line_surfbrightness for line l (core.py:986-1003, base_class.py:275-277): no guards
+__device__ __forceinline__ double rb_surf(const MolDev &mol, const WarpMem &w, int l, const SolveCfg &cfg) {
+  const double xnu = mol.xnu[l];
+  const double ftau = exp(-w.taul[l]);
+  const double earg = cfg.fk_epi * xnu / w.tex[l];
+  const double bnutex = cfg.thc_epi * (xnu * xnu * xnu) / (exp(earg) - 1.0);
+  const double toti = w.backi[l] * ftau + bnutex * (1.0 - ftau);
+  return toti - w.backi[l];
+}
+
+struct SolveIO {
+  long long n;
+  const double *tkin, *dens, *cdmol;
+  double *xpop, *tex, *tau, *surf;
+  int *niter, *status;
+  unsigned long long *counters;
+};
+
+__global__ void __launch_bounds__(256) k_lvg_solve_v1(MolDev mol, SolveCfg cfg, SolveIO io) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nl = mol.nlev, nn = mol.nline;
+  const WarpMem w = carve(smem + (size_t)wib * v1_warp_doubles(nl, nn), nl, nn);
+  unsigned long long iters = 0;
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(&io.counters[0], 1ULL);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if ((long long)idx >= io.n) break;
+    double dens[RB_MAXPART];
+    for (int p = 0; p < mol.npart; ++p) dens[p] = io.dens[idx * mol.npart + p];
+    int st = 0;
+    const int it = v1_solve(mol, w, lane, io.tkin[idx], dens, io.cdmol[idx], cfg, &st);
+    const bool bad = (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) != 0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    int nonfinite = 0;
+    for (int l = lane; l < nn; l += 32) {
+      const double s = bad ? qnan : rb_surf(mol, w, l, cfg);
+      if (!bad && !isfinite(s)) nonfinite = 1;
+      if (io.surf) io.surf[idx * nn + l] = s;
+      if (io.tex) io.tex[idx * nn + l] = bad ? qnan : w.tex[l];
+      if (io.tau) io.tau[idx * nn + l] = bad ? qnan : w.taul[l];
+    }
+    if (io.xpop)
+      for (int i = lane; i < nl; i += 32) io.xpop[idx * nl + i] = bad ? qnan : w.xpop[i];
+    nonfinite = __any_sync(0xffffffffu, nonfinite);
+    if (nonfinite) st |= RB_ST_NONFINITE;
+    if (lane == 0) {
+      if (io.niter) io.niter[idx] = it;
+      if (io.status) io.status[idx] = st;
+    }
+    // pyradex calls matrix() for it = 0..it inclusive unless it stopped at maxiter
+    iters += bad ? 0 : (unsigned long long)((st & RB_ST_MAXITER) ? it : it + 1);
+    __syncwarp();
+  }
+  if (lane == 0 && iters) {
+    atomicAdd(&io.counters[1], iters);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused lnprob kernels: prior -> (1 or 2) solves -> line fluxes -> chi^2
+// ------------------------------------------------------------------------------------------------
+struct LnprobIO {
+  long long n;
+  const double *P;       // n x (4*NCOMP)
+  double *lnp;           // n
+  rb_obs obs;
+  double bounds[16];     // (4*NCOMP) x 2
+  int has_td;
+  double t_d;
+  unsigned long long *counters;
+};
+
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+
+// lnprior, one component (emcee/emcee_radex.py:169-175)
+__device__ double lnprior1(const double *p, const double *b) {
+  for (int i = 0; i < 4; ++i)
+    if (p[i] > b[2 * i + 1] || p[i] < b[2 * i]) return neg_inf();
+  const double d = p[2] - p[0];
+  if (d >= 17.5 || d <= 10.0) return neg_inf();
+  return 0.0;
+}
+
+// lnprior, two components (emcee/emcee_radex_2comp.py:199-234)
+__device__ double lnprior2(const double *p, const double *b, int has_td, double t_d) {
+  for (int i = 0; i < 8; ++i)
+    if (p[i] > b[2 * i + 1] || p[i] < b[2 * i]) return neg_inf();
+  if (p[5] <= p[1]) return neg_inf();
+  const double d1 = p[2] - p[0], d2 = p[6] - p[4];
+  if (d1 >= 18.0 || d1 <= 9.0 || d2 >= 18.0 || d2 <= 9.0) return neg_inf();
+  if (p[3] < p[7]) return neg_inf();
+  double logp = 0.0;
+  for (int i = 0; i < 8; ++i) {
+    if (i == 1 && has_td) {
+      const double tk = pow(10.0, p[i]);
+      if (t_d <= 0.0) return neg_inf();
+      const double sigma = 1.0 * t_d;
+      const double z = (tk - t_d) / sigma;
+      logp += (-0.5 * (z * z) - log(sigma * sqrt(2.0 * 3.141592653589793)));
+    } else {
+      logp += -(b[2 * i + 1] - b[2 * i]);
+    }
+  }
+  return logp;
+}
+
+template <int NCOMP>
+__global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, LnprobIO io) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nl = mol.nlev, nn = mol.nline;
+  const WarpMem w = carve(smem + (size_t)wib * v1_warp_doubles(nl, nn), nl, nn);
+  constexpr int ND = 4 * NCOMP;
+  const double fortho = 3.0 / (1.0 + 3.0);  // opr = 3 (emcee_radex.py:95-96)
+  unsigned long long iters = 0, solves = 0;
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(&io.counters[0], 1ULL);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if ((long long)idx >= io.n) break;
+    double p[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) p[i] = io.P[idx * ND + i];
+    const double lp = (NCOMP == 1) ? lnprior1(p, io.bounds) : lnprior2(p, io.bounds, io.has_td, io.t_d);
+    double result = neg_inf();
+    if (isfinite(lp)) {  // prior short-circuit: no solve (emcee_radex.py:178-180)
+      double model = 0.0;  // lane i < nobs holds the model flux of observed line i
+      bool value_error = false;
+#pragma unroll
+      for (int c = 0; c < NCOMP; ++c) {
+        if (value_error) break;
+        const double dens_tot = pow(10.0, p[4 * c + 0]);
+        double dens[RB_MAXPART];
+        for (int q = 0; q < mol.npart; ++q)
+          dens[q] = (mol.part_id[q] == 2) ? (1.0 - fortho) * dens_tot : (mol.part_id[q] == 3) ? fortho * dens_tot : 0.0;
+        int st = 0;
+        const int it = v1_solve(mol, w, lane, pow(10.0, p[4 * c + 1]), dens, pow(10.0, p[4 * c + 2]), cfg, &st);
+        if (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) {
+          value_error = true;  // ValueError -> -inf (emcee_radex.py:134-137)
+        } else {
+          ++solves;
+          iters += (unsigned long long)((st & RB_ST_MAXITER) ? it : it + 1);
+          if (lane < io.obs.nobs) {
+            const double s = rb_surf(mol, w, io.obs.jup[lane] - 1, cfg);
+            model += s * pow(10.0, p[4 * c + 3]) * 1.0e23;  // x size [sr] x 1 km/s -> Jy km/s
+          }
+        }
+        __syncwarp();
+      }
+      if (!value_error) {
+        // lnlike (emcee_radex.py:132-167 / emcee_radex_2comp.py:169-196)
+        int bad = 0;
+        double r2 = 0.0, le = 0.0;
+        if (lane < io.obs.nobs) {
+          const double f = io.obs.flux[lane];
+          const double e = fmax(fabs(io.obs.eflux[lane]), 1.0e-12);
+          if (!isfinite(f) || !isfinite(model) || !isfinite(e)) {
+            bad = 1;
+          } else {
+            const double r = (f - model) / e;
+            const double max_safe = 1.3407807929942596e+153;  // sqrt(DBL_MAX)/10
+            if (!isfinite(r) || fabs(r) > max_safe) bad = 1;
+            r2 = r * r;
+            le = log(e);
+          }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        const double chi2 = warp_sum(r2), logterm = 2.0 * warp_sum(le);
+        if (!bad) {
+          const double ll = -0.5 * (chi2 + logterm);
+          result = isfinite(ll) ? lp + ll : neg_inf();
+        }
+      }
+    }
+    if (lane == 0) io.lnp[idx] = result;
+  }
+  if (lane == 0) {
+    if (iters) atomicAdd(&io.counters[1], iters);
+    if (solves) atomicAdd(&io.counters[2], solves);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stretch move (emcee StretchMove / RedBlueMove) with Philox4x32-10
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {  // 53-bit uniform in [0,1)
+  const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+  return (double)(v >> 11) * 1.1102230246251565e-16;
+}
+
+__global__ void k_stretch_propose(long long ns, int ndim, const double *S, long long nc, const double *C, double a,
+                                  unsigned long long seed, unsigned long long step, int half, long long gid0,
+                                  long long gid_stride, double *Q, double *logfac) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= ns) return;
+  const unsigned long long gid = (unsigned long long)(gid0 + k * gid_stride);
+  uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(step * 2ULL + (unsigned)half),
+                   (uint32_t)((step * 2ULL + (unsigned)half) >> 32) & 0x7fffffffu};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const double u = u01(c[0], c[1]);
+  // explicit roundings (no FMA contraction) so a host restatement reproduces the proposal bit for bit
+  const double sq = __dadd_rn(__dmul_rn(a - 1.0, u), 1.0);
+  const double z = __dmul_rn(sq, sq) / a;
+  long long j = (long long)(u01(c[2], c[3]) * (double)nc);
+  if (j >= nc) j = nc - 1;
+  for (int d = 0; d < ndim; ++d) {
+    const double cj = C[j * ndim + d], s = S[k * ndim + d];
+    Q[k * ndim + d] = __dsub_rn(cj, __dmul_rn(cj - s, z));
+  }
+  logfac[k] = (ndim - 1.0) * log(z);
+}
+
+__global__ void k_stretch_accept(long long ns, int ndim, double *S, double *lnp_old, const double *Q,
+                                 const double *lnp_new, const double *logfac, unsigned long long seed,
+                                 unsigned long long step, int half, long long gid0, long long gid_stride,
+                                 unsigned long long *naccept) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  int acc = 0;
+  if (k < ns) {
+    const unsigned long long gid = (unsigned long long)(gid0 + k * gid_stride);
+    uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(step * 2ULL + (unsigned)half),
+                     ((uint32_t)((step * 2ULL + (unsigned)half) >> 32) & 0x7fffffffu) | 0x80000000u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double lnu = log(u01(c[0], c[1]));
+    const double lnew = lnp_new[k];
+    const double lnpdiff = logfac[k] + lnew - lnp_old[k];
+    // emcee: accepted = lnpdiff > log(u).  -inf - -inf = NaN compares false -> rejected, like numpy.
+    if (lnpdiff > lnu) {
+      acc = 1;
+      for (int d = 0; d < ndim; ++d) S[k * ndim + d] = Q[k * ndim + d];
+      lnp_old[k] = lnew;
+    }
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0 && ballot && naccept) atomicAdd(naccept, (unsigned long long)__popc(ballot));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <typename T>
+int upload(rb_ctx *ctx, const std::vector<T> &v, const T **out) {
+  void *d = nullptr;
+  const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  ctx->owned.push_back(d);
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<const T *>(d);
+  return RB_OK;
+}
+
+SolveCfg make_cfg(const rb_opts *o, double deltav_kms, double tbg, int geometry) {
+  rb_opts d;
+  rb_default_opts(&d);
+  if (o) d = *o;
+  SolveCfg c;
+  c.deltav_cms = deltav_kms * 1.0e5;  // km/s -> cm/s (core.py:447-454)
+  c.tbg = tbg;
+  c.method = geometry;
+  c.stop_rule = d.stop_rule;
+  c.miniter = d.miniter;
+  c.maxiter = d.maxiter;
+  c.abs_tol = d.abs_tol;
+  c.fk_epi = d.fk_epi;
+  c.thc_epi = d.thc_epi;
+  return c;
+}
+
+int check_common(rb_ctx *ctx, double deltav_kms, double tbg, int geometry) {
+  if (!ctx) {
+    rb_set_error("null context");
+    return RB_ERR_ARG;
+  }
+  if (geometry < 1 || geometry > 3) {
+    rb_set_error("Invalid escapeProbGeom, must be one of lvg,sphere,slab");
+    return RB_ERR_ARG;
+  }
+  if (!(deltav_kms > 0.0) || !(tbg > 0.0)) {
+    rb_set_error("deltav and tbg must be positive");
+    return RB_ERR_ARG;
+  }
+  return RB_OK;
+}
+
+struct Launch {
+  int warps_per_block;
+  int blocks;
+  size_t smem;
+};
+
+Launch v1_launch(rb_ctx *ctx, long long n) {
+  const size_t per_warp = v1_warp_doubles(ctx->mol.nlev, ctx->mol.nline) * sizeof(double);
+  int wpb = (int)(((size_t)ctx->smem_optin - 1024) / per_warp);
+  if (wpb > 8) wpb = 8;
+  if (wpb < 1) wpb = 1;
+  Launch L;
+  L.warps_per_block = wpb;
+  L.smem = per_warp * wpb;
+  long long need = (n + wpb - 1) / wpb;
+  L.blocks = (int)std::min<long long>(need, ctx->sm_count);
+  if (L.blocks < 1) L.blocks = 1;
+  return L;
+}
+
+int ensure_scratch(rb_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return RB_OK;
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  ctx->scratch = nullptr;
+  ctx->scratch_bytes = 0;
+  const size_t want = bytes + bytes / 4;
+  CUDA_TRY(cudaMalloc(&ctx->scratch, want));
+  ctx->scratch_bytes = want;
+  return RB_OK;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace
+
+extern "C" {
+
+void rb_default_opts(rb_opts *o) {
+  if (!o) return;
+  o->stop_rule = RB_STOP_PYRADEX;
+  o->miniter = 10;
+  o->maxiter = 200;
+  o->kernel = 0;
+  o->abs_tol = 1e-16;
+  // astropy (CODATA 2018) h c / k_B and 2 h c in cgs, which is what core.py:981-984 evaluates to
+  o->fk_epi = 1.4387768775039338;
+  o->thc_epi = 3.9728917142978115e-16;
+}
+
+int rb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
+  if (!mol || !out) {
+    rb_set_error("rb_ctx_create: null argument");
+    return RB_ERR_ARG;
+  }
+  *out = nullptr;
+  if (mol->nlev > RB_MAXLEV) {
+    rb_set_error("molecule has more levels than RB_MAXLEV");
+    return RB_ERR_LIMIT;
+  }
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) {
+    rb_set_error("no such CUDA device");
+    return RB_ERR_CUDA;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    rb_set_error("libradex_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    return RB_ERR_CUDA;
+  }
+  rb_ctx *ctx = new rb_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    rb_set_error("cudaStreamCreate failed");
+    delete ctx;
+    return RB_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  MolDev &m = ctx->mol;
+  m.nlev = mol->nlev;
+  m.nline = mol->nline;
+  m.npart = mol->npart;
+  int rc = RB_OK;
+#define UP(vec, dst)                                  \
+  if (rc == RB_OK) rc = upload(ctx, vec, &dst);
+  UP(mol->eterm, m.eterm);
+  UP(mol->gstat, m.gstat);
+  UP(mol->iupp, m.iupp);
+  UP(mol->ilow, m.ilow);
+  UP(mol->aeinst, m.aeinst);
+  UP(mol->xnu, m.xnu);
+  // CSR of lines incident on each level, in line order (keeps the reference's summation order)
+  std::vector<int> ptr(mol->nlev + 1, 0), idx;
+  for (int i = 0; i < mol->nlev; ++i) {
+    for (int l = 0; l < mol->nline; ++l) {
+      if (mol->iupp[l] == i) idx.push_back(l | 0x40000000);
+      if (mol->ilow[l] == i) idx.push_back(l);
+    }
+    ptr[i + 1] = (int)idx.size();
+  }
+  UP(ptr, m.lev_ptr);
+  UP(idx, m.lev_line);
+  for (int p = 0; p < mol->npart && rc == RB_OK; ++p) {
+    const rb_mol::Partner &pt = mol->partners[p];
+    m.part_id[p] = pt.id;
+    m.ntemp[p] = pt.ntemp;
+    m.ncoll[p] = pt.ncoll;
+    UP(pt.temps, m.temps[p]);
+    UP(pt.lcu, m.lcu[p]);
+    UP(pt.lcl, m.lcl[p]);
+    UP(pt.rates_tc, m.rates_tc[p]);
+  }
+#undef UP
+  if (rc == RB_OK && cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+    rb_set_error("cudaMalloc(counters) failed");
+    rc = RB_ERR_CUDA;
+  }
+  if (rc == RB_OK) {
+    const Launch L = v1_launch(ctx, 1 << 20);
+    cudaError_t e = cudaFuncSetAttribute(k_lvg_solve_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (e != cudaSuccess) {
+      rb_set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+      rc = RB_ERR_CUDA;
+    }
+  }
+  if (rc != RB_OK) {
+    rb_ctx_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return RB_OK;
+}
+
+void rb_ctx_destroy(rb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (void *p : ctx->owned) cudaFree(p);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->counters) cudaFree(ctx->counters);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int rb_ctx_sync(rb_ctx *ctx) {
+  if (!ctx) return RB_ERR_ARG;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return RB_OK;
+}
+
+int rb_ctx_set_stream(rb_ctx *ctx, void *stream) {
+  if (!ctx) return RB_ERR_ARG;
+  ctx->stream = stream ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
+  return RB_OK;
+}
+
+int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double *dens, const double *cdmol,
+                       double deltav_kms, double tbg, int geometry, const rb_opts *opts, double *xpop,
+                       double *tex, double *tau, double *surf, int32_t *niter, int32_t *status) {
+  int rc = check_common(ctx, deltav_kms, tbg, geometry);
+  if (rc != RB_OK) return rc;
+  if (n < 0 || (n > 0 && (!tkin || !dens || !cdmol))) {
+    rb_set_error("rb_solve_batch: null input");
+    return RB_ERR_ARG;
+  }
+  if (n == 0) return RB_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const SolveCfg cfg = make_cfg(opts, deltav_kms, tbg, geometry);
+  CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  SolveIO io{n, tkin, dens, cdmol, xpop, tex, tau, surf, niter, status, ctx->counters};
+  const Launch L = v1_launch(ctx, n);
+  k_lvg_solve_v1<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+int rb_solve_batch(rb_ctx *ctx, int64_t n, const double *tkin, const double *dens, const double *cdmol,
+                   double deltav_kms, double tbg, int geometry, const rb_opts *opts, double *xpop, double *tex,
+                   double *tau, double *surf, int32_t *niter, int32_t *status) {
+  int rc = check_common(ctx, deltav_kms, tbg, geometry);
+  if (rc != RB_OK) return rc;
+  if (n < 0 || (n > 0 && (!tkin || !dens || !cdmol))) {
+    rb_set_error("rb_solve_batch: null input");
+    return RB_ERR_ARG;
+  }
+  if (n == 0) return RB_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int nl = ctx->mol.nlev, nn = ctx->mol.nline, np = ctx->mol.npart;
+  const size_t b_t = align256(n * sizeof(double)), b_d = align256((size_t)n * np * sizeof(double));
+  const size_t b_x = xpop ? align256((size_t)n * nl * sizeof(double)) : 0;
+  const size_t b_l = align256((size_t)n * nn * sizeof(double));
+  const size_t b_i = align256(n * sizeof(int32_t));
+  const size_t total = 2 * b_t + b_d + b_x + (tex ? b_l : 0) + (tau ? b_l : 0) + (surf ? b_l : 0) + 2 * b_i;
+  rc = ensure_scratch(ctx, total);
+  if (rc != RB_OK) return rc;
+  char *p = static_cast<char *>(ctx->scratch);
+  double *d_t = (double *)p; p += b_t;
+  double *d_c = (double *)p; p += b_t;
+  double *d_d = (double *)p; p += b_d;
+  double *d_x = nullptr, *d_tex = nullptr, *d_tau = nullptr, *d_s = nullptr;
+  if (xpop) { d_x = (double *)p; p += b_x; }
+  if (tex) { d_tex = (double *)p; p += b_l; }
+  if (tau) { d_tau = (double *)p; p += b_l; }
+  if (surf) { d_s = (double *)p; p += b_l; }
+  int32_t *d_it = (int32_t *)p; p += b_i;
+  int32_t *d_st = (int32_t *)p; p += b_i;
+  cudaStream_t s = ctx->stream;
+  CUDA_TRY(cudaMemcpyAsync(d_t, tkin, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(d_c, cdmol, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(d_d, dens, (size_t)n * np * sizeof(double), cudaMemcpyHostToDevice, s));
+  rc = rb_solve_batch_dev(ctx, n, d_t, d_d, d_c, deltav_kms, tbg, geometry, opts, d_x, d_tex, d_tau, d_s, d_it, d_st);
+  if (rc != RB_OK) return rc;
+  if (xpop) CUDA_TRY(cudaMemcpyAsync(xpop, d_x, (size_t)n * nl * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (tex) CUDA_TRY(cudaMemcpyAsync(tex, d_tex, (size_t)n * nn * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (tau) CUDA_TRY(cudaMemcpyAsync(tau, d_tau, (size_t)n * nn * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (surf) CUDA_TRY(cudaMemcpyAsync(surf, d_s, (size_t)n * nn * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (niter) CUDA_TRY(cudaMemcpyAsync(niter, d_it, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, d_st, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  unsigned long long cnt[3] = {0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(cnt, ctx->counters, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  ctx->last_total_iters = (long long)cnt[1];
+  return RB_OK;
+}
+
+static int lnprob_dev(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const rb_obs *obs, const double *bounds,
+                      int has_td, double t_d, double tbg, const rb_opts *opts, double *lnp) {
+  int rc = check_common(ctx, 1.0, tbg, RB_GEOM_LVG);
+  if (rc != RB_OK) return rc;
+  if (n < 0 || !obs || !bounds || (n > 0 && (!P || !lnp))) {
+    rb_set_error("rb_lnprob: null argument");
+    return RB_ERR_ARG;
+  }
+  if (obs->nobs < 1 || obs->nobs > RB_MAX_OBS) {
+    rb_set_error("rb_lnprob: nobs must be in 1..RB_MAX_OBS");
+    return RB_ERR_ARG;
+  }
+  for (int i = 0; i < obs->nobs; ++i)
+    if (obs->jup[i] < 1 || obs->jup[i] > ctx->mol.nline) {
+      rb_set_error("rb_lnprob: Jup outside the molecule's line list");
+      return RB_ERR_ARG;
+    }
+  if (n == 0) return RB_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const SolveCfg cfg = make_cfg(opts, 1.0, tbg, RB_GEOM_LVG);  // deltav=1 km/s, LVG (emcee_radex.py:108-117)
+  CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  LnprobIO io;
+  memset(&io, 0, sizeof(io));
+  io.n = n;
+  io.P = P;
+  io.lnp = lnp;
+  io.obs = *obs;
+  memcpy(io.bounds, bounds, sizeof(double) * 8 * ncomp);
+  io.has_td = has_td;
+  io.t_d = t_d;
+  io.counters = ctx->counters;
+  const Launch L = v1_launch(ctx, n);
+  if (ncomp == 1)
+    k_lnprob_v1<1><<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  else
+    k_lnprob_v1<2><<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+static int lnprob_host(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const rb_obs *obs, const double *bounds,
+                       int has_td, double t_d, double tbg, const rb_opts *opts, double *lnp, int64_t *nsolves) {
+  if (!ctx) {
+    rb_set_error("null context");
+    return RB_ERR_ARG;
+  }
+  if (n < 0 || (n > 0 && (!P || !lnp))) {
+    rb_set_error("rb_lnprob: null argument");
+    return RB_ERR_ARG;
+  }
+  if (n == 0) {
+    if (nsolves) *nsolves = 0;
+    return RB_OK;
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t b_p = align256((size_t)n * 4 * ncomp * sizeof(double)), b_l = align256(n * sizeof(double));
+  int rc = ensure_scratch(ctx, b_p + b_l);
+  if (rc != RB_OK) return rc;
+  double *d_p = (double *)ctx->scratch;
+  double *d_l = (double *)((char *)ctx->scratch + b_p);
+  cudaStream_t s = ctx->stream;
+  CUDA_TRY(cudaMemcpyAsync(d_p, P, (size_t)n * 4 * ncomp * sizeof(double), cudaMemcpyHostToDevice, s));
+  rc = lnprob_dev(ctx, ncomp, n, d_p, obs, bounds, has_td, t_d, tbg, opts, d_l);
+  if (rc != RB_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(lnp, d_l, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  unsigned long long cnt[3] = {0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(cnt, ctx->counters, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  ctx->last_total_iters = (long long)cnt[1];
+  if (nsolves) *nsolves = (int64_t)cnt[2];
+  return RB_OK;
+}
+
+int rb_lnprob1(rb_ctx *ctx, int64_t n, const double *P, const rb_obs *obs, const double *bounds, double tbg,
+               const rb_opts *opts, double *lnp, int64_t *nsolves) {
+  return lnprob_host(ctx, 1, n, P, obs, bounds, 0, 0.0, tbg, opts, lnp, nsolves);
+}
+
+int rb_lnprob2(rb_ctx *ctx, int64_t n, const double *P, const rb_obs *obs, const double *bounds, int has_td,
+               double t_d, double tbg, const rb_opts *opts, double *lnp, int64_t *nsolves) {
+  return lnprob_host(ctx, 2, n, P, obs, bounds, has_td, t_d, tbg, opts, lnp, nsolves);
+}
+
+static int copy_nsolves(rb_ctx *ctx, int64_t *nsolves_dev) {
+  if (nsolves_dev)
+    CUDA_TRY(cudaMemcpyAsync(nsolves_dev, ctx->counters + 2, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  return RB_OK;
+}
+
+int rb_lnprob1_dev(rb_ctx *ctx, int64_t n, const double *P, const rb_obs *obs, const double *bounds, double tbg,
+                   const rb_opts *opts, double *lnp, int64_t *nsolves_dev) {
+  int rc = lnprob_dev(ctx, 1, n, P, obs, bounds, 0, 0.0, tbg, opts, lnp);
+  if (rc != RB_OK || n == 0) return rc;
+  return copy_nsolves(ctx, nsolves_dev);
+}
+
+int rb_lnprob2_dev(rb_ctx *ctx, int64_t n, const double *P, const rb_obs *obs, const double *bounds, int has_td,
+                   double t_d, double tbg, const rb_opts *opts, double *lnp, int64_t *nsolves_dev) {
+  int rc = lnprob_dev(ctx, 2, n, P, obs, bounds, has_td, t_d, tbg, opts, lnp);
+  if (rc != RB_OK || n == 0) return rc;
+  return copy_nsolves(ctx, nsolves_dev);
+}
+
+int rb_stretch_propose_dev(rb_ctx *ctx, int64_t ns, int32_t ndim, const double *S, int64_t nc, const double *C,
+                           double a, uint64_t seed, uint64_t step, int32_t half, int64_t gid0, int64_t gid_stride,
+                           double *Q, double *logfac) {
+  if (!ctx || ns < 0 || nc < 1 || ndim < 1 || !S || !C || !Q || !logfac || !(a > 1.0)) {
+    rb_set_error("rb_stretch_propose_dev: bad argument");
+    return RB_ERR_ARG;
+  }
+  if (ns == 0) return RB_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int tpb = 256;
+  const int blocks = (int)((ns + tpb - 1) / tpb);
+  k_stretch_propose<<<blocks, tpb, 0, ctx->stream>>>(ns, ndim, S, nc, C, a, seed, step, half, gid0, gid_stride, Q, logfac);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+int rb_stretch_accept_dev(rb_ctx *ctx, int64_t ns, int32_t ndim, double *S, double *lnp_old, const double *Q,
+                          const double *lnp_new, const double *logfac, uint64_t seed, uint64_t step, int32_t half,
+                          int64_t gid0, int64_t gid_stride, int64_t *naccept) {
+  if (!ctx || ns < 0 || ndim < 1 || !S || !lnp_old || !Q || !lnp_new || !logfac) {
+    rb_set_error("rb_stretch_accept_dev: bad argument");
+    return RB_ERR_ARG;
+  }
+  if (ns == 0) return RB_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int tpb = 256;
+  const int blocks = (int)((ns + tpb - 1) / tpb);
+  k_stretch_accept<<<blocks, tpb, 0, ctx->stream>>>(ns, ndim, S, lnp_old, Q, lnp_new, logfac, seed, step, half, gid0, gid_stride,
+                                                    reinterpret_cast<unsigned long long *>(naccept));
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+int rb_ctx_counters(rb_ctx *ctx, int64_t *total_iters_last, int64_t *launches_total) {
+  if (!ctx) return RB_ERR_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  unsigned long long cnt[3] = {0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(cnt, ctx->counters, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->last_total_iters = (long long)cnt[1];
+  if (total_iters_last) *total_iters_last = ctx->last_total_iters;
+  if (launches_total) *launches_total = ctx->launches;
+  return RB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MOLFILE = os.path.join(ROOT, "radex_emcee_b200", "data", "co.dat")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def molfile():
+    return MOLFILE
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle.oracle import Oracle
+    return Oracle(MOLFILE)
+
+
+@pytest.fixture(scope="session")
+def golden_solve():
+    return np.load(os.path.join(GOLDEN, "macho_solve.npz"))
+
+
+def draw_params(rng, n, tbg, lo_n=2.0, hi_n=7.0, lo_N=15.5, hi_N=19.5):
+    """Config-2 draws."""
+    out = np.empty((0, 3))
+    while out.shape[0] < n:
+        ln = rng.uniform(lo_n, hi_n, 2 * n)
+        lt = rng.uniform(np.log10(tbg), 3.0, 2 * n)
+        lN = rng.uniform(lo_N, hi_N, 2 * n)
+        ok = (lN - ln > 10.0) & (lN - ln < 17.5)
+        out = np.vstack([out, np.column_stack([10 ** lt, 10 ** ln, 10 ** lN])[ok]])
+    return out[:n]
