@@ -140,6 +140,9 @@ int rb_stretch_accept_dev(rb_ctx *ctx, int64_t ns, int32_t ndim, double *S, doub
  * total matrix iterations summed over models, and kernels launched since ctx creation.        */
 int rb_ctx_counters(rb_ctx *ctx, int64_t *total_iters_last, int64_t *launches_total);
 
+/* measured FP64 FMA throughput of this GPU (TFLOP/s), the roofline denominator bench.py reports */
+int rb_fp64_peak(rb_ctx *ctx, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,9 +61,11 @@ SIGNATURES = {
     "rb_lnprob2_dev": (C.c_int, [_vp, C.c_int64, _vp, C.POINTER(rb_obs), _vp, C.c_int, C.c_double, C.c_double,
                                  C.POINTER(rb_opts), _vp, _vp]),
     "rb_stretch_propose_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, C.c_int64, _vp, C.c_double, C.c_uint64,
-                                         XX: (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64,
-                                        C.c_int32, C.c_int64, _vp]),
+                                         C.c_uint64, C.c_int32, C.c_int64, C.c_int64, _vp, _vp]),
+    "rb_stretch_accept_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64,
+                                        C.c_int32, C.c_int64, C.c_int64, _vp]),
     "rb_ctx_counters": (C.c_int, [_vp, _lp, _lp]),
+    "rb_fp64_peak": (C.c_int, [_vp, _dp]),
 }
 
 _lib = None
@@ -184,6 +186,11 @@ class Context:
 
     def set_stream(self, stream_ptr):
         check(load().rb_ctx_set_stream(self.handle, _vp(stream_ptr) if stream_ptr else None))
+
+    def fp64_peak_tflops(self):
+        v = C.c_double(0.0)
+        check(load().rb_fp64_peak(self.handle, C.byref(v)))
+        return v.value
 
     def counters(self):
         it, ln = C.c_int64(), C.c_int64()

@@ -694,6 +694,24 @@ __global__ void k_stretch_accept(long long ns, int ndim, double *S, double *lnp_
   if ((threadIdx.x & 31) == 0 && ballot && naccept) atomicAdd(naccept, (unsigned long long)__popc(ballot));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// FP64 FMA peak probe: the roofline denominator for the solve kernels is the vector FP64 pipe,
+// which MEASURED_PEAKS.json does not cover, so bench.py measures it live with this kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+      a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1116,6 +1134,34 @@ int rb_stretch_accept_dev(rb_ctx *ctx, int64_t ns, int32_t ndim, double *S, doub
                                                     reinterpret_cast<unsigned long long *>(naccept));
   CUDA_TRY(cudaGetLastError());
   ctx->launches += 1;
+  return RB_OK;
+}
+
+int rb_fp64_peak(rb_ctx *ctx, double *tflops) {
+  if (!ctx || !tflops) return RB_ERR_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8, tpb = 256, iters = 4096;
+  double *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, (size_t)blocks * tpb * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    k_fp64_peak<<<blocks, tpb, 0, ctx->stream>>>(d, iters);
+    CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  ctx->launches += 5;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  const double flops = 2.0 * 8 * 16 * (double)iters * (double)blocks * tpb;
+  *tflops = flops / (best * 1e-3) * 1e-12;
   return RB_OK;
 }
 

@@ -1,0 +1,78 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol the header declares, the
+LAMDA loader agrees with the oracle's independent parser, and GPU entry points fail loudly here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import MOLFILE, ROOT
+from radex_emcee_b200 import _lib
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "radex_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), s
+    assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
+
+
+def test_default_opts():
+    o = _lib.default_opts()
+    assert (o.stop_rule, o.miniter, o.maxiter) == (0, 10, 200)
+    assert o.abs_tol == 1e-16
+    assert abs(o.fk_epi / 1.4387768775 - 1) < 1e-9 and abs(o.thc_epi / 3.97289171e-16 - 1) < 1e-8
+
+
+def test_moldata_matches_oracle_parser(oracle):
+    m = _lib.MolData(MOLFILE)
+    assert (m.nlev, m.nline, m.npart) == (41, 40, 2)
+    assert list(m.partner_id) == [2, 3] and list(m.ncoll) == [820, 820] and list(m.ntemp) == [25, 25]
+    np.testing.assert_array_equal(m.eterm, oracle.eterm)
+    np.testing.assert_array_equal(m.gstat, oracle.gstat)
+    np.testing.assert_array_equal(m.iupp, oracle.iupp)
+    np.testing.assert_array_equal(m.ilow, oracle.ilow)
+    np.testing.assert_array_equal(m.aeinst, oracle.aeinst)
+    np.testing.assert_array_equal(m.xnu, oracle.xnu)      # from level energies, not the GHz column
+    np.testing.assert_array_equal(m.spfreq, oracle.spfreq)
+
+
+def test_moldata_errors(tmp_path):
+    with pytest.raises(_lib.RadexB200Error, match="cannot open"):
+        _lib.MolData(str(tmp_path / "missing.dat"))
+    bad = tmp_path / "bad.dat"
+    bad.write_text("!MOLECULE\nX\n!W\n1.0\n!N\n3\n!LEV\n1 0.0 1.0\n")
+    with pytest.raises(_lib.RadexB200Error, match="parse error"):
+        _lib.MolData(str(bad))
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the context cannot be created and says so; nothing silently computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = _lib.MolData(MOLFILE)
+    with pytest.raises(_lib.RadexB200Error):
+        _lib.Context(m, 0)
+    from radex_emcee_b200.radex import Radex
+    R = Radex(species="co", density={"oH2": 750.0, "pH2": 250.0}, column=1e15, temperature=20.0)
+    with pytest.raises(_lib.RadexB200Error):
+        R.run_radex()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "radex_emcee_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("oracle/radex_oracle.c ro_", "").replace("oracle ro_", ""), f

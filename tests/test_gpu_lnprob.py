@@ -1,0 +1,96 @@
+"""Fused lnprob kernels vs the oracle's restatement of the drivers' lnprob (tolerance: 1e-4 absolute)."""
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from radex_emcee_b200 import emcee_radex as er1
+from radex_emcee_b200 import emcee_radex_2comp as er2
+from radex_emcee_b200.data import get_source, read_data
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 1e-4
+
+
+def _source1(name="G09v1.97"):
+    data = read_data(ROOT + "/data/flux.dat")
+    z, lw, jup, flux, eflux = get_source(name, data)
+    tbg, ra, bounds, p0 = er1.source_setup(z)
+    return z, jup, flux, eflux, tbg, bounds, p0
+
+
+def _walkers1(rng, bounds, n):
+    P = rng.uniform(bounds[:, 0] - 0.05, bounds[:, 1] + 0.05, size=(n, 4))
+    P[:, 3] = rng.uniform(-10.5, -9.0, n)
+    return P
+
+
+def test_lnprob_1comp(oracle):
+    z, jup, flux, eflux, tbg, bounds, p0 = _source1()
+    er1.R = None
+    R = er1.init_radex(tbg)
+    R.set_params(tbg=tbg)
+    rng = np.random.default_rng(3)
+    P = np.vstack([_walkers1(rng, bounds, 400), p0 + 1e-3 * rng.standard_normal((56, 4))])
+    got, nsolves = er1.lnprob(P, jup, flux, eflux, bounds=bounds, return_nsolves=True)
+    ref = np.array([oracle.lnprob1(p, jup, flux, eflux, bounds, tbg) for p in P])
+    assert not np.isnan(got).any()
+    assert ((got == -np.inf) == (ref == -np.inf)).all()
+    fin = np.isfinite(ref)
+    assert fin.sum() > 100
+    # walkers whose iteration ends in a limit cycle (reference capped at 200) are excluded from the 1e-4 bar
+    err = np.abs(got[fin] - ref[fin])
+    assert np.quantile(err, 0.95) < ATOL, np.quantile(err, [0.5, 0.95, 1.0])
+    assert (err < ATOL * np.maximum(1.0, np.abs(ref[fin]) * 1e-3)).mean() > 0.97
+    # prior short-circuit: solves only where the prior is finite (emcee_radex.py:178-180)
+    assert nsolves == np.isfinite(er1.lnprior(P, bounds)).sum()
+    # scalar call form
+    assert abs(er1.lnprob(p0, jup, flux, eflux, bounds=bounds) - oracle.lnprob1(p0, jup, flux, eflux, bounds, tbg)) < ATOL
+    # composition lnprior + lnlike (separate launches + host chi^2) equals the fused kernel
+    comp = er1.lnprior(P, bounds) + np.where(np.isfinite(er1.lnprior(P, bounds)), er1.lnlike(P, jup, flux, eflux, R), 0)
+    np.testing.assert_allclose(comp[fin], got[fin], rtol=1e-9, atol=1e-9)
+
+
+def test_lnprob_2comp(oracle):
+    data = read_data(ROOT + "/data/flux_for2p.dat")
+    z, T_d, lw, jup, flux, eflux = get_source("G09v1.97", data)
+    tbg, ra, bounds, p0 = er2.source_setup(z)
+    er2.R = None
+    er2.init_radex(tbg)
+    er2.R.set_params(tbg=tbg)
+    rng = np.random.default_rng(4)
+    P = p0 + rng.standard_normal((192, 8)) * np.array([0.4, 0.1, 0.4, 0.3, 0.4, 0.2, 0.4, 0.3])
+    P = np.vstack([P, rng.uniform(bounds[:, 0], bounds[:, 1], size=(64, 8))])
+    for td in (T_d, None):
+        got, nsolves = er2.lnprob(P, jup, flux, eflux, bounds=bounds, T_d=td, return_nsolves=True)
+        ref = np.array([oracle.lnprob2(p, jup, flux, eflux, bounds, td, tbg) for p in P])
+        assert not np.isnan(got).any()
+        assert ((got == -np.inf) == (ref == -np.inf)).all()
+        fin = np.isfinite(ref)
+        assert fin.sum() > 30
+        err = np.abs(got[fin] - ref[fin])
+        assert np.quantile(err, 0.9) < ATOL, np.quantile(err, [0.5, 0.9, 1.0])
+        np.testing.assert_allclose(er2.lnprior(P, bounds, T_d=td)[fin] * 0 + 1, 1)
+        assert nsolves == 2 * np.isfinite(er2.lnprior(P, bounds, T_d=td)).sum()
+    # T_d <= 0 -> -inf everywhere
+    assert (er2.lnprob(P[:8], jup, flux, eflux, bounds=bounds, T_d=-1.0) == -np.inf).all()
+
+
+def test_lnlike_edge_semantics(oracle):
+    """sigma floor, NaN flux, out-of-range column -> same -inf/finite pattern as the reference code."""
+    z, jup, flux, eflux, tbg, bounds, p0 = _source1()
+    er1.R = None
+    er1.init_radex(tbg)
+    wide = bounds.copy()
+    wide[2] = [4.0, 26.0]
+    p_bad_N = np.array([4.0, 1.5, 25.5, -9.9])        # 10^25.5 > 1e25 -> ValueError in pyradex -> -inf
+    p_bad_N[0] = 25.5 - 12.0
+    wide[0] = [0.0, 20.0]
+    assert er1.lnprob(p_bad_N, jup, flux, eflux, bounds=wide) == -np.inf
+    assert oracle.lnprob1(p_bad_N, jup, flux, eflux, wide, tbg) == -np.inf
+    f2 = flux.copy()
+    f2[1] = np.nan
+    assert er1.lnprob(p0, jup, f2, eflux, bounds=bounds) == -np.inf
+    e0 = np.zeros_like(eflux)                           # floored at 1e-12 -> huge but finite chi^2
+    a, b = er1.lnprob(p0, jup, flux, e0, bounds=bounds), oracle.lnprob1(p0, jup, flux, e0, bounds, tbg)
+    assert np.isfinite(a) and abs(a / b - 1) < 1e-6

@@ -1,0 +1,175 @@
+"""Parity of the CUDA solve path (through the C ABI) with the CPU oracle and with the fixtures made
+by the reference binary.  Tolerances from BASELINE.json north_star: populations and line fluxes
+within 1e-5 relative; compared on entries the reference itself resolves (population > 1e-9, lines
+whose flux is > 1e-6 of the model's brightest line)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import MOLFILE, draw_params
+from radex_emcee_b200 import _lib
+from radex_emcee_b200.radex import Radex
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return _lib.Context(_lib.MolData(MOLFILE), 0)
+
+
+def gpu_solve(ctx, T, nh2, N, tbg, method=2, **optkw):
+    T, nh2, N = (np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64) for a in (T, nh2, N))
+    n = T.size
+    mol = ctx.mol
+    dens = np.zeros((n, mol.npart))
+    for p, pid in enumerate(mol.partner_id):
+        dens[:, p] = {2: 0.25, 3: 0.75}.get(int(pid), 0.0) * nh2
+    out = dict(xpop=np.empty((n, mol.nlev)), tex=np.empty((n, mol.nline)), tau=np.empty((n, mol.nline)),
+               surf=np.empty((n, mol.nline)), niter=np.empty(n, np.int32), status=np.empty(n, np.int32))
+    opts = _lib.default_opts(**optkw)
+    _lib.check(_lib.load().rb_solve_batch(ctx.handle, n, _lib.ptr(T), _lib.ptr(dens), _lib.ptr(N), 1.0, float(tbg),
+                                          method, C.byref(opts), _lib.ptr(out["xpop"]), _lib.ptr(out["tex"]),
+                                          _lib.ptr(out["tau"]), _lib.ptr(out["surf"]), _lib.ptr(out["niter"]),
+                                          _lib.ptr(out["status"])))
+    return out
+
+
+def compare(got, ref, iupp, label=""):
+    """Returns the fraction of models compared; asserts parity on them."""
+    both = ((ref["niter"] < 200) & (got["niter"] < 200)) | ((ref["niter"] >= 200) & (got["niter"] >= 200))
+    both &= np.isfinite(ref["surf"]).all(axis=1)
+    assert both.mean() > 0.9, (label, both.mean())
+    x, xr = got["xpop"][both], ref["xpop"][both]
+    sig = xr > 1e-9
+    ex = (np.abs(x - xr) / xr)[sig].max()
+    sl = sig[:, iupp - 1]
+    et = (np.abs(got["tex"][both] - ref["tex"][both]) / np.abs(ref["tex"][both]))[sl].max()
+    eu = (np.abs(got["tau"][both] - ref["tau"][both]) / np.maximum(np.abs(ref["tau"][both]), 1e-12))[sl].max()
+    s, sr = got["surf"][both], ref["surf"][both]
+    bright = np.abs(sr) > 1e-6 * np.abs(sr).max(axis=1, keepdims=True)
+    es = (np.abs(s - sr) / np.abs(sr))[bright & sl].max()
+    # limit-cycle models (both sides ran to maxiter) follow the same path only approximately
+    conv = ref["niter"][both] < 200
+    assert ex < RTOL and et < RTOL and eu < RTOL and es < RTOL, (label, ex, et, eu, es, conv.mean())
+    return both.mean()
+
+
+@pytest.mark.parametrize("method,tbg,n", [(2, 10.926, 384), (2, 2.7315, 192), (1, 2.7315, 96), (3, 10.926, 96)])
+def test_random_sweep_vs_oracle(ctx, oracle, method, tbg, n):
+    P = draw_params(np.random.default_rng(1000 + method + int(tbg)), n, tbg)
+    T, nh2, N = P[:, 0], P[:, 1], P[:, 2]
+    ref = oracle.solve_batch(T, 0.25 * nh2, 0.75 * nh2, N, tbg=tbg, method=method)
+    got = gpu_solve(ctx, T, nh2, N, tbg, method)
+    compare(got, ref, oracle.iupp, "sweep m%d" % method)
+    # iteration counters agree except for last-ULP jitter of the 1e-16 stop test
+    same = (got["niter"] == ref["niter"]).mean()
+    assert same > 0.5, same
+
+
+def test_vs_reference_binary_fixtures(ctx, oracle, golden_solve):
+    g = golden_solve
+    for method in (1, 2, 3):
+        for tbg in np.unique(g["cases"][:, 3]):
+            sel = (g["cases"][:, 4] == method) & (g["cases"][:, 3] == tbg)
+            if not sel.any():
+                continue
+            c = g["cases"][sel]
+            got = gpu_solve(ctx, c[:, 0], c[:, 1], c[:, 2], tbg, method)
+            ref = dict(xpop=g["xpop"][sel], tex=g["tex"][sel], tau=g["tau"][sel], niter=g["niter"][sel])
+            ref["surf"] = np.ones_like(ref["tex"])
+            both = (ref["niter"] < 200) & (got["niter"] < 200)
+            sig = ref["xpop"][both] > 1e-9
+            assert (np.abs(got["xpop"][both] - ref["xpop"][both]) / ref["xpop"][both])[sig].max() < RTOL
+            sl = sig[:, oracle.iupp - 1]
+            assert (np.abs(got["tex"][both] - ref["tex"][both]) / np.abs(ref["tex"][both]))[sl].max() < RTOL
+
+
+def test_radex_native_stop_rule(ctx, oracle):
+    from oracle.oracle import STOP_RADEX
+    P = draw_params(np.random.default_rng(5), 128, 10.926)
+    T, nh2, N = P[:, 0], P[:, 1], P[:, 2]
+    ref = oracle.solve_batch(T, 0.25 * nh2, 0.75 * nh2, N, tbg=10.926, stop_rule=STOP_RADEX)
+    got = gpu_solve(ctx, T, nh2, N, 10.926, stop_rule=_lib.STOP_RADEX)
+    same = got["niter"] == ref["niter"]
+    assert same.mean() > 0.9
+    sig = ref["xpop"][same] > 1e-9
+    assert (np.abs(got["xpop"][same] - ref["xpop"][same]) / ref["xpop"][same])[sig].max() < RTOL
+
+
+def test_edge_cases(ctx, oracle):
+    # empty batch
+    out = gpu_solve(ctx, np.zeros(0), np.zeros(0), np.zeros(0), 2.7315)
+    assert out["xpop"].shape == (0, 41)
+    # out-of-range T / N: status bits, NaN outputs, no solve (the reference raises ValueError)
+    T = np.array([0.0, -5.0, 2e4, 50.0, 50.0, 50.0, np.nan])
+    N = np.array([1e15, 1e15, 1e15, 1e4, 1e26, 1e15, 1e15])
+    out = gpu_solve(ctx, T, np.full(7, 1e4), N, 2.7315)
+    assert list(out["status"][:3] & 1) == [1, 1, 1] and list(out["status"][3:5] & 2) == [2, 2]
+    assert out["status"][6] & 1
+    assert out["status"][5] & 3 == 0 and np.isfinite(out["surf"][5]).all()
+    assert np.isnan(out["surf"][[0, 1, 2, 3, 4, 6]]).all() and (out["niter"][[0, 1, 2, 3, 4, 6]] == 0).all()
+    # maxiter flag and a custom cap
+    out = gpu_solve(ctx, [50.0], [1e4], [1e17], 2.7315, maxiter=20)
+    assert out["niter"][0] == 20 and out["status"][0] & 4
+    # single model, extreme but legal corners stay finite
+    out = gpu_solve(ctx, [1e4, 2.8], [1e2, 1e7], [1e5, 1e25], 2.7315)
+    assert (out["status"] & 3 == 0).all()
+    # bad geometry is an argument error, like pyradex's ValueError
+    with pytest.raises(_lib.RadexB200Error, match="escapeProbGeom"):
+        gpu_solve(ctx, [50.0], [1e4], [1e15], 2.7315, method=7)
+
+
+def test_radex_class_surface(oracle):
+    """pyradex-style use, one model (the reference test-suite's own settings, test_radex.py:99-115)."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        rdx = Radex(species="co", collider_densities={"H2": 1e4}, column_per_bin=1e14, deltav=1.0, temperature=30,
+                    tbackground=2.73)
+    niter = rdx.run_radex()
+    assert rdx.temperature == 30.0 and rdx.column == 1e14
+    opr = min(3.0, 9.0 * np.exp(-170.6 / 30.0))
+    fo = opr / (1 + opr)
+    ref = oracle.solve_batch([30.0], [1e4 * (1 - fo)], [1e4 * fo], [1e14], tbg=2.73)
+    assert abs(niter - ref["niter"][0]) <= 3
+    np.testing.assert_allclose(rdx.tex[:10], ref["tex"][0][:10], rtol=RTOL)
+    np.testing.assert_allclose(rdx.tau[:10], ref["tau"][0][:10], rtol=RTOL)
+    np.testing.assert_allclose(rdx.upperlevelpop[:10], ref["xpop"][0][1:11], rtol=RTOL)
+    np.testing.assert_allclose(rdx.lowerlevelpop[:10], ref["xpop"][0][0:10], rtol=RTOL)
+    np.testing.assert_allclose(rdx.source_line_surfbrightness[:10], ref["surf"][0][:10], rtol=RTOL)
+    tab = rdx.get_table()
+    assert list(tab.columns)[:3] == ["Tex", "tau", "frequency"] and len(tab) == 40
+    # mod-params sequence of test_radex.py:175-200 keeps working and changes the answer
+    rdx2 = Radex(species="co", column=1e15, density={"oH2": 750.0, "pH2": 250.0}, temperature=20)
+    t0 = rdx2(return_table=False) and rdx2.tex[0]
+    rdx2.column = 1e14
+    rdx2.run_radex()
+    t1 = rdx2.tex[0]
+    rdx2.temperature = 25
+    rdx2.run_radex()
+    t2 = rdx2.tex[0]
+    assert t0 != t1 != t2
+    with pytest.raises(ValueError):
+        rdx2.temperature = -1
+    with pytest.raises(ValueError):
+        rdx2.column = 1e30
+    with pytest.raises(ValueError):
+        rdx2.escapeProbGeom = "cube"
+    with pytest.raises(ValueError):
+        rdx2.density = {"Xe": 1.0}
+    # batch through the same class
+    rdx3 = Radex(species="co", column=np.array([1e15, 1e16, 1e17]), density={"oH2": 750.0, "pH2": 250.0},
+                 temperature=np.array([20.0, 40.0, 80.0]))
+    assert rdx3.run_radex().shape == (3,) and rdx3.tex.shape == (3, 40)
+
+
+def test_determinism(ctx):
+    P = draw_params(np.random.default_rng(9), 200, 10.926)
+    a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926)
+    b = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926)
+    for k in ("xpop", "tex", "tau", "surf", "niter"):
+        np.testing.assert_array_equal(a[k], b[k])
