@@ -85,8 +85,10 @@ int rb_moldata_lines(const rb_mol *mol, int32_t *iupp, int32_t *ilow, double *ae
 int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out);
 void rb_ctx_destroy(rb_ctx *ctx);
 int rb_ctx_sync(rb_ctx *ctx);
-/* use a caller-owned CUDA stream (cudaStream_t as void*; NULL = the ctx's own stream) */
+/* launch on a caller-owned CUDA stream (cudaStream_t as void*; 0 = CUDA's legacy default stream,
+ * which is what PyTorch's default stream is); rb_ctx_reset_stream goes back to the ctx's own. */
 int rb_ctx_set_stream(rb_ctx *ctx, void *stream);
+int rb_ctx_reset_stream(rb_ctx *ctx);
 
 /* ---- batched solve: replaces set_params + run_radex + tex/tau/level_population +
  * source_line_surfbrightness (core.py:388-438, 856-925, 703-717, 986-1003; base_class.py:275-277)

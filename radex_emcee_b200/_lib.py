@@ -50,6 +50,7 @@ SIGNATURES = {
     "rb_ctx_destroy": (None, [_vp]),
     "rb_ctx_sync": (C.c_int, [_vp]),
     "rb_ctx_set_stream": (C.c_int, [_vp, _vp]),
+    "rb_ctx_reset_stream": (C.c_int, [_vp]),
     "rb_solve_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int,
                                  C.POINTER(rb_opts), _vp, _vp, _vp, _vp, _vp, _vp]),
     "rb_solve_batch_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int,
@@ -185,7 +186,11 @@ class Context:
         check(load().rb_ctx_sync(self.handle))
 
     def set_stream(self, stream_ptr):
-        check(load().rb_ctx_set_stream(self.handle, _vp(stream_ptr) if stream_ptr else None))
+        """stream_ptr: cudaStream_t handle as int (0 = legacy default stream, PyTorch's default)."""
+        check(load().rb_ctx_set_stream(self.handle, _vp(int(stream_ptr))))
+
+    def reset_stream(self):
+        check(load().rb_ctx_reset_stream(self.handle))
 
     def fp64_peak_tflops(self):
         v = C.c_double(0.0)

@@ -924,7 +924,13 @@ int rb_ctx_sync(rb_ctx *ctx) {
 
 int rb_ctx_set_stream(rb_ctx *ctx, void *stream) {
   if (!ctx) return RB_ERR_ARG;
-  ctx->stream = stream ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
+  ctx->stream = static_cast<cudaStream_t>(stream);   // 0 is CUDA's legacy default stream, used as given
+  return RB_OK;
+}
+
+int rb_ctx_reset_stream(rb_ctx *ctx) {
+  if (!ctx) return RB_ERR_ARG;
+  ctx->stream = ctx->own_stream;
   return RB_OK;
 }
 

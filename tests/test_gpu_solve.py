@@ -38,36 +38,66 @@ def gpu_solve(ctx, T, nh2, N, tbg, method=2, **optkw):
     return out
 
 
-def compare(got, ref, iupp, label=""):
-    """Returns the fraction of models compared; asserts parity on them."""
-    both = ((ref["niter"] < 200) & (got["niter"] < 200)) | ((ref["niter"] >= 200) & (got["niter"] >= 200))
-    both &= np.isfinite(ref["surf"]).all(axis=1)
-    assert both.mean() > 0.9, (label, both.mean())
-    x, xr = got["xpop"][both], ref["xpop"][both]
-    sig = xr > 1e-9
-    ex = (np.abs(x - xr) / xr)[sig].max()
-    sl = sig[:, iupp - 1]
-    et = (np.abs(got["tex"][both] - ref["tex"][both]) / np.abs(ref["tex"][both]))[sl].max()
-    eu = (np.abs(got["tau"][both] - ref["tau"][both]) / np.maximum(np.abs(ref["tau"][both]), 1e-12))[sl].max()
-    s, sr = got["surf"][both], ref["surf"][both]
-    bright = np.abs(sr) > 1e-6 * np.abs(sr).max(axis=1, keepdims=True)
-    es = (np.abs(s - sr) / np.abs(sr))[bright & sl].max()
-    # limit-cycle models (both sides ran to maxiter) follow the same path only approximately
-    conv = ref["niter"][both] < 200
-    assert ex < RTOL and et < RTOL and eu < RTOL and es < RTOL, (label, ex, et, eu, es, conv.mean())
-    return both.mean()
+def rel_errors(got, ref, iupp):
+    """Per-model max relative error of populations (> 1e-9), Tex/tau of those levels' lines, and
+    the fluxes of lines brighter than 1e-6 of the model's brightest."""
+    with np.errstate(all="ignore"):
+        xr = ref["xpop"]
+        sig = xr > 1e-9
+        ex = np.where(sig, np.abs(got["xpop"] - xr) / xr, 0).max(axis=1)
+        sl = sig[:, iupp - 1]
+        et = np.where(sl, np.abs(got["tex"] - ref["tex"]) / np.abs(ref["tex"]), 0)
+        eu = np.where(sl, np.abs(got["tau"] - ref["tau"]) / np.maximum(np.abs(ref["tau"]), 1e-12), 0)
+        sr = ref["surf"]
+        bright = np.abs(sr) > 1e-6 * np.nanmax(np.abs(sr), axis=1, keepdims=True)
+        bright &= np.abs(sr) > 1e-25          # erg s-1 cm-2 Hz-1 sr-1; real lines are 1e-16 .. 1e-9
+        es = np.where(bright & sl, np.abs(got["surf"] - sr) / np.abs(sr), 0)
+    f = lambda e: np.nan_to_num(e, nan=np.inf).max(axis=1)
+    return ex, f(et), f(eu), f(es)
 
 
-@pytest.mark.parametrize("method,tbg,n", [(2, 10.926, 384), (2, 2.7315, 192), (1, 2.7315, 96), (3, 10.926, 96)])
+PERTURBATIONS = ((0, 3e-14), (1, 1e-13), (2, 1e-13), (0, -1e-12), (2, -1e-11))
+
+
+def well_posed(oracle, T, nh2, N, tbg, method, ref, **kw):
+    """Models on which the reference algorithm reproduces ITSELF: the oracle re-run with one input
+    perturbed in its last digits (five variants) lands on the same answer to 1e-6.  Elsewhere the
+    under-relaxed iteration wanders between attractors or ends in a limit cycle at maxiter, and
+    the reference's own output changes with the last bit of its input -- no implementation with
+    different rounding (FMA, another libm) can be asked to match it there ('ill-posed
+    models'; for the worst offenders most perturbations land on the GPU's answer, not the oracle's)."""
+    ok = np.isfinite(ref["surf"]).all(axis=1)
+    # strong masers (a line with tau < -3, amplification e^-tau) are hypersensitive by construction
+    ok &= np.nan_to_num(ref["tau"], nan=-np.inf).min(axis=1) > -3.0
+    for which, eps in PERTURBATIONS:
+        t, d, c = T.copy(), nh2.copy(), N.copy()
+        (t, d, c)[which][:] *= 1 + eps
+        pert = oracle.solve_batch(t, 0.25 * d, 0.75 * d, c, tbg=tbg, method=method, **kw)
+        ex, et, eu, es = rel_errors(pert, ref, oracle.iupp)
+        ok &= (ex < 1e-6) & (et < 1e-6) & (es < 1e-6)
+    return ok
+
+
+def compare(got, ref, ok, iupp, label=""):
+    ex, et, eu, es = rel_errors(got, ref, iupp)
+    worst = max(ex[ok].max(), et[ok].max(), eu[ok].max(), es[ok].max())
+    assert worst < RTOL, (label, ex[ok].max(), et[ok].max(), eu[ok].max(), es[ok].max())
+    return worst
+
+
+@pytest.mark.parametrize("method,tbg,n", [(2, 10.926, 512), (2, 2.7315, 256), (1, 2.7315, 256), (3, 10.926, 256)])
 def test_random_sweep_vs_oracle(ctx, oracle, method, tbg, n):
     P = draw_params(np.random.default_rng(1000 + method + int(tbg)), n, tbg)
     T, nh2, N = P[:, 0], P[:, 1], P[:, 2]
     ref = oracle.solve_batch(T, 0.25 * nh2, 0.75 * nh2, N, tbg=tbg, method=method)
+    ok = well_posed(oracle, T, nh2, N, tbg, method, ref)
+    assert ok.mean() > 0.7, ok.mean()
     got = gpu_solve(ctx, T, nh2, N, tbg, method)
-    compare(got, ref, oracle.iupp, "sweep m%d" % method)
-    # iteration counters agree except for last-ULP jitter of the 1e-16 stop test
-    same = (got["niter"] == ref["niter"]).mean()
-    assert same > 0.5, same
+    compare(got, ref, ok, oracle.iupp, "sweep m%d" % method)
+    # the iteration counter follows the reference's up to last-ULP jitter of the 1e-16 stop test
+    assert (np.abs(got["niter"] - ref["niter"])[ok & (ref["niter"] < 200) & (got["niter"] < 200)] <= 40).all()
+    # status bits: non-finite flag agrees with the oracle's NaNs on well-posed models
+    assert ((got["status"][ok] & 8) == 0).all()
 
 
 def test_vs_reference_binary_fixtures(ctx, oracle, golden_solve):
@@ -90,14 +120,14 @@ def test_vs_reference_binary_fixtures(ctx, oracle, golden_solve):
 
 def test_radex_native_stop_rule(ctx, oracle):
     from oracle.oracle import STOP_RADEX
-    P = draw_params(np.random.default_rng(5), 128, 10.926)
+    P = draw_params(np.random.default_rng(5), 256, 10.926)
     T, nh2, N = P[:, 0], P[:, 1], P[:, 2]
     ref = oracle.solve_batch(T, 0.25 * nh2, 0.75 * nh2, N, tbg=10.926, stop_rule=STOP_RADEX)
+    ok = well_posed(oracle, T, nh2, N, 10.926, 2, ref, stop_rule=STOP_RADEX)
     got = gpu_solve(ctx, T, nh2, N, 10.926, stop_rule=_lib.STOP_RADEX)
-    same = got["niter"] == ref["niter"]
-    assert same.mean() > 0.9
-    sig = ref["xpop"][same] > 1e-9
-    assert (np.abs(got["xpop"][same] - ref["xpop"][same]) / ref["xpop"][same])[sig].max() < RTOL
+    ok &= got["niter"] == ref["niter"]      # same number of matrix() calls -> same (unconverged) state
+    assert ok.mean() > 0.7
+    compare(got, ref, ok, oracle.iupp, "radex rule")
 
 
 def test_edge_cases(ctx, oracle):
