@@ -276,7 +276,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "models_per_gpu": n, "l2": "256 MiB flush write between timed steps",
-                       "outputs": "xpop,tex,tau,surf,niter,status", "kernel": "k_lvg_solve_v1"},
+                       "outputs": "xpop,tex,tau,surf,niter,status", "kernel": "k_lvg_solve_v2"},
             "iters_per_solve": iters_all / (world * n),
             "matrix_iterations_per_s": iters_all / (ms_per_step * 1e-3),
             "frac_at_maxiter": float((status_host & 4).astype(bool).mean()),

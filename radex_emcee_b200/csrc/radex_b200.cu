@@ -453,6 +453,8 @@ __device__ __forceinline__ double rb_surf(const MolDev &mol, const WarpMem &w, i
   return toti - w.backi[l];
 }
 
+#include "lvg_v2.cuh"
+
 struct SolveIO {
   long long n;
   const double *tkin, *dens, *cdmol;
@@ -596,6 +598,136 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
       }
       if (!value_error) {
         // lnlike (emcee_radex.py:132-167 / emcee_radex_2comp.py:169-196)
+        int bad = 0;
+        double r2 = 0.0, le = 0.0;
+        if (lane < io.obs.nobs) {
+          const double f = io.obs.flux[lane];
+          const double e = fmax(fabs(io.obs.eflux[lane]), 1.0e-12);
+          if (!isfinite(f) || !isfinite(model) || !isfinite(e)) {
+            bad = 1;
+          } else {
+            const double r = (f - model) / e;
+            const double max_safe = 1.3407807929942596e+153;  // sqrt(DBL_MAX)/10
+            if (!isfinite(r) || fabs(r) > max_safe) bad = 1;
+            r2 = r * r;
+            le = log(e);
+          }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        const double chi2 = warp_sum(r2), logterm = 2.0 * warp_sum(le);
+        if (!bad) {
+          const double ll = -0.5 * (chi2 + logterm);
+          result = isfinite(ll) ? lp + ll : neg_inf();
+        }
+      }
+    }
+    if (lane == 0) io.lnp[idx] = result;
+  }
+  if (lane == 0) {
+    if (iters) atomicAdd(&io.counters[1], iters);
+    if (solves) atomicAdd(&io.counters[2], solves);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// v2 kernels (41-level molecules): register-resident GTH elimination with DMMA updates
+// ------------------------------------------------------------------------------------------------
+#define V2_WARPS 9
+
+__global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, SolveCfg cfg, SolveIO io) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double *sm = smem + (size_t)wib * v2::SLAB;
+  const int nl = mol.nlev, nn = mol.nline;
+  unsigned long long iters = 0;
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(&io.counters[0], 1ULL);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if ((long long)idx >= io.n) break;
+    double dens[RB_MAXPART];
+#pragma unroll
+    for (int p = 0; p < RB_MAXPART; ++p) dens[p] = (p < mol.npart) ? io.dens[idx * mol.npart + p] : 0.0;
+    int st = 0;
+    v2::LineRegs L;
+    const int it = v2::solve(mol, sm, lane, io.tkin[idx], dens, io.cdmol[idx], cfg, L, &st);
+    const bool bad = (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) != 0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    int nonfinite = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int l = lane + 32 * h;
+      if (l < nn) {
+        const double sf = bad ? qnan : v2::surf(L, h, cfg);
+        if (!bad && !isfinite(sf)) nonfinite = 1;
+        if (io.surf) io.surf[idx * nn + l] = sf;
+        if (io.tex) io.tex[idx * nn + l] = bad ? qnan : L.tex[h];
+        if (io.tau) io.tau[idx * nn + l] = bad ? qnan : L.tau[h];
+      }
+    }
+    if (io.xpop)
+      for (int i = lane; i < nl; i += 32) io.xpop[idx * nl + i] = bad ? qnan : sm[v2::O_X + i];
+    nonfinite = __any_sync(0xffffffffu, nonfinite);
+    if (nonfinite) st |= RB_ST_NONFINITE;
+    if (lane == 0) {
+      if (io.niter) io.niter[idx] = it;
+      if (io.status) io.status[idx] = st;
+    }
+    iters += bad ? 0 : (unsigned long long)((st & RB_ST_MAXITER) ? it : it + 1);
+    __syncwarp();
+  }
+  if (lane == 0 && iters) atomicAdd(&io.counters[1], iters);
+}
+
+template <int NCOMP>
+__global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lnprob_v2(MolDev mol, SolveCfg cfg, LnprobIO io) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double *sm = smem + (size_t)wib * v2::SLAB;
+  constexpr int ND = 4 * NCOMP;
+  const double fortho = 3.0 / (1.0 + 3.0);  // opr = 3 (emcee_radex.py:95-96)
+  unsigned long long iters = 0, solves = 0;
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(&io.counters[0], 1ULL);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if ((long long)idx >= io.n) break;
+    double p[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) p[i] = io.P[idx * ND + i];
+    const double lp = (NCOMP == 1) ? lnprior1(p, io.bounds) : lnprior2(p, io.bounds, io.has_td, io.t_d);
+    double result = neg_inf();
+    if (isfinite(lp)) {  // prior short-circuit: no solve (emcee_radex.py:178-180)
+      double model = 0.0;
+      bool value_error = false;
+#pragma unroll
+      for (int c = 0; c < NCOMP; ++c) {
+        if (value_error) break;
+        const double dens_tot = pow(10.0, p[4 * c + 0]);
+        double dens[RB_MAXPART];
+#pragma unroll
+        for (int q = 0; q < RB_MAXPART; ++q)
+          dens[q] = (q < mol.npart && mol.part_id[q] == 2) ? (1.0 - fortho) * dens_tot
+                    : (q < mol.npart && mol.part_id[q] == 3) ? fortho * dens_tot : 0.0;
+        int st = 0;
+        v2::LineRegs L;
+        const int it = v2::solve(mol, sm, lane, pow(10.0, p[4 * c + 1]), dens, pow(10.0, p[4 * c + 2]), cfg, L, &st);
+        if (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) {
+          value_error = true;  // ValueError -> -inf (emcee_radex.py:134-137)
+        } else {
+          ++solves;
+          iters += (unsigned long long)((st & RB_ST_MAXITER) ? it : it + 1);
+          // line fluxes through a small shared staging area (the panel-row buffer is free now)
+          double *stage = sm + v2::O_QROW;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (L.on[h]) stage[lane + 32 * h] = v2::surf(L, h, cfg);
+          __syncwarp();
+          if (lane < io.obs.nobs) model += stage[io.obs.jup[lane] - 1] * pow(10.0, p[4 * c + 3]) * 1.0e23;
+        }
+        __syncwarp();
+      }
+      if (!value_error) {
         int bad = 0;
         double r2 = 0.0, le = 0.0;
         if (lane < io.obs.nobs) {
@@ -781,6 +913,20 @@ Launch v1_launch(rb_ctx *ctx, long long n) {
   return L;
 }
 
+bool use_v2(const rb_ctx *ctx, const rb_opts *o) {
+  const int kernel = o ? o->kernel : 0;
+  return kernel != 1 && ctx->mol.nlev == v2::NL && ctx->mol.nline <= v2::MAXLINE;
+}
+
+Launch v2_launch(rb_ctx *ctx, long long n) {
+  Launch L;
+  L.warps_per_block = V2_WARPS;
+  L.smem = (size_t)V2_WARPS * v2::SLAB * sizeof(double);
+  const long long need = (n + V2_WARPS - 1) / V2_WARPS;
+  L.blocks = (int)std::max<long long>(1, std::min<long long>(need, ctx->sm_count));
+  return L;
+}
+
 int ensure_scratch(rb_ctx *ctx, size_t bytes) {
   if (bytes <= ctx->scratch_bytes) return RB_OK;
   if (ctx->scratch) cudaFree(ctx->scratch);
@@ -893,6 +1039,12 @@ int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
     cudaError_t e = cudaFuncSetAttribute(k_lvg_solve_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (mol->nlev == v2::NL && mol->nline <= v2::MAXLINE) {
+      const int sm2 = (int)(V2_WARPS * v2::SLAB * sizeof(double));
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_solve_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
+    }
     if (e != cudaSuccess) {
       rb_set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       rc = RB_ERR_CUDA;
@@ -948,8 +1100,13 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
   const SolveCfg cfg = make_cfg(opts, deltav_kms, tbg, geometry);
   CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
   SolveIO io{n, tkin, dens, cdmol, xpop, tex, tau, surf, niter, status, ctx->counters};
-  const Launch L = v1_launch(ctx, n);
-  k_lvg_solve_v1<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  if (use_v2(ctx, opts)) {
+    const Launch L = v2_launch(ctx, n);
+    k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  } else {
+    const Launch L = v1_launch(ctx, n);
+    k_lvg_solve_v1<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  }
   CUDA_TRY(cudaGetLastError());
   ctx->launches += 1;
   return RB_OK;
@@ -1035,11 +1192,19 @@ static int lnprob_dev(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const 
   io.has_td = has_td;
   io.t_d = t_d;
   io.counters = ctx->counters;
-  const Launch L = v1_launch(ctx, n);
-  if (ncomp == 1)
-    k_lnprob_v1<1><<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
-  else
-    k_lnprob_v1<2><<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  if (use_v2(ctx, opts)) {
+    const Launch L = v2_launch(ctx, n);
+    if (ncomp == 1)
+      k_lnprob_v2<1><<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+    else
+      k_lnprob_v2<2><<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  } else {
+    const Launch L = v1_launch(ctx, n);
+    if (ncomp == 1)
+      k_lnprob_v1<1><<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+    else
+      k_lnprob_v1<2><<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  }
   CUDA_TRY(cudaGetLastError());
   ctx->launches += 1;
   return RB_OK;
