@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
 // ------------------------------------------------------------------------------------------------
 // v2 kernels (41-level molecules): register-resident GTH elimination with DMMA updates
 // ------------------------------------------------------------------------------------------------
-#define V2_WARPS 9
+#define V2_WARPS 8
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, SolveCfg cfg, SolveIO io) {
   extern __shared__ double smem[];
