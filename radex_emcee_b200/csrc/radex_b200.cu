@@ -55,6 +55,7 @@ struct MolDev {
 };
 
 struct SolveCfg {
+  double *bslab;   // v2: per-warp global copies of the collisional matrix (L2-resident)
   double deltav_cms, tbg;
   int method, stop_rule, miniter, maxiter;
   double abs_tol, fk_epi, thc_epi;
@@ -72,6 +73,7 @@ struct rb_ctx {
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
   unsigned long long *counters = nullptr; // [0] work queue head, [1] total iterations, [2] solves
+  double *bslab = nullptr;                // v2: sm_count x V2_WARPS x NB doubles
   long long launches = 0;
   long long last_total_iters = 0;
 };
@@ -632,12 +634,16 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
 // ------------------------------------------------------------------------------------------------
 // v2 kernels (41-level molecules): register-resident GTH elimination with DMMA updates
 // ------------------------------------------------------------------------------------------------
-#define V2_WARPS 8
+#define V2_WARPS 12
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, SolveCfg cfg, SolveIO io) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double *sm = smem + (size_t)wib * v2::SLAB;
+  double *gB = cfg.bslab + ((size_t)blockIdx.x * V2_WARPS + wib) * v2::NB;
+  unsigned phase = 0;
+  if (lane == 0) v2::mbar_init(sm + v2::O_MBAR, 1);
+  __syncwarp();
   const int nl = mol.nlev, nn = mol.nline;
   unsigned long long iters = 0;
   for (;;) {
@@ -650,7 +656,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
     for (int p = 0; p < RB_MAXPART; ++p) dens[p] = (p < mol.npart) ? io.dens[idx * mol.npart + p] : 0.0;
     int st = 0;
     v2::LineRegs L;
-    const int it = v2::solve(mol, sm, lane, io.tkin[idx], dens, io.cdmol[idx], cfg, L, &st);
+    const int it = v2::solve(mol, sm, gB, phase, lane, io.tkin[idx], dens, io.cdmol[idx], cfg, L, &st);
     const bool bad = (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) != 0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     int nonfinite = 0;
@@ -684,6 +690,10 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lnprob_v2(MolDev mol, Solv
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double *sm = smem + (size_t)wib * v2::SLAB;
+  double *gB = cfg.bslab + ((size_t)blockIdx.x * V2_WARPS + wib) * v2::NB;
+  unsigned phase = 0;
+  if (lane == 0) v2::mbar_init(sm + v2::O_MBAR, 1);
+  __syncwarp();
   constexpr int ND = 4 * NCOMP;
   const double fortho = 3.0 / (1.0 + 3.0);  // opr = 3 (emcee_radex.py:95-96)
   unsigned long long iters = 0, solves = 0;
@@ -711,7 +721,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lnprob_v2(MolDev mol, Solv
                     : (q < mol.npart && mol.part_id[q] == 3) ? fortho * dens_tot : 0.0;
         int st = 0;
         v2::LineRegs L;
-        const int it = v2::solve(mol, sm, lane, pow(10.0, p[4 * c + 1]), dens, pow(10.0, p[4 * c + 2]), cfg, L, &st);
+        const int it = v2::solve(mol, sm, gB, phase, lane, pow(10.0, p[4 * c + 1]), dens, pow(10.0, p[4 * c + 2]), cfg, L, &st);
         if (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) {
           value_error = true;  // ValueError -> -inf (emcee_radex.py:134-137)
         } else {
@@ -860,11 +870,12 @@ int upload(rb_ctx *ctx, const std::vector<T> &v, const T **out) {
   return RB_OK;
 }
 
-SolveCfg make_cfg(const rb_opts *o, double deltav_kms, double tbg, int geometry) {
+SolveCfg make_cfg(const rb_ctx *ctx, const rb_opts *o, double deltav_kms, double tbg, int geometry) {
   rb_opts d;
   rb_default_opts(&d);
   if (o) d = *o;
   SolveCfg c;
+  c.bslab = ctx->bslab;
   c.deltav_cms = deltav_kms * 1.0e5;  // km/s -> cm/s (core.py:447-454)
   c.tbg = tbg;
   c.method = geometry;
@@ -1044,6 +1055,8 @@ int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_solve_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
+      if (e == cudaSuccess)
+        e = cudaMalloc(&ctx->bslab, (size_t)ctx->sm_count * V2_WARPS * v2::NB * sizeof(double));
     }
     if (e != cudaSuccess) {
       rb_set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
@@ -1064,6 +1077,7 @@ void rb_ctx_destroy(rb_ctx *ctx) {
   for (void *p : ctx->owned) cudaFree(p);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->counters) cudaFree(ctx->counters);
+  if (ctx->bslab) cudaFree(ctx->bslab);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1097,7 +1111,7 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
   }
   if (n == 0) return RB_OK;
   CUDA_TRY(cudaSetDevice(ctx->device));
-  const SolveCfg cfg = make_cfg(opts, deltav_kms, tbg, geometry);
+  const SolveCfg cfg = make_cfg(ctx, opts, deltav_kms, tbg, geometry);
   CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
   SolveIO io{n, tkin, dens, cdmol, xpop, tex, tau, surf, niter, status, ctx->counters};
   if (use_v2(ctx, opts)) {
@@ -1180,7 +1194,7 @@ static int lnprob_dev(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const 
     }
   if (n == 0) return RB_OK;
   CUDA_TRY(cudaSetDevice(ctx->device));
-  const SolveCfg cfg = make_cfg(opts, 1.0, tbg, RB_GEOM_LVG);  // deltav=1 km/s, LVG (emcee_radex.py:108-117)
+  const SolveCfg cfg = make_cfg(ctx, opts, 1.0, tbg, RB_GEOM_LVG);  // deltav=1 km/s, LVG (emcee_radex.py:108-117)
   CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
   LnprobIO io;
   memset(&io, 0, sizeof(io));
