@@ -41,7 +41,8 @@ def test_lnprob_1comp(oracle):
     # compared where the reference reproduces itself under a 1e-13 perturbation of the walker (see
     # test_gpu_solve.well_posed); chi^2 can be ~1e6, so the bar is 1e-4 absolute or 1e-9 relative
     ref2 = np.array([oracle.lnprob1(p, jup, flux, eflux, bounds, tbg) for p in P + 1e-13])
-    ok = fin & (np.abs(ref2 - ref) < 1e-7 * np.maximum(1.0, np.abs(ref)))
+    with np.errstate(invalid="ignore"):
+        ok = fin & (np.abs(ref2 - ref) < 1e-7 * np.maximum(1.0, np.abs(ref))) & (np.abs(ref) < 1e12)   # 1e12: maser blow-ups
     assert ok.sum() > 0.7 * fin.sum()
     err = np.abs(got[ok] - ref[ok])
     assert (err < np.maximum(ATOL, 1e-9 * np.abs(ref[ok]))).all(), err.max()
@@ -72,7 +73,8 @@ def test_lnprob_2comp(oracle):
         fin = np.isfinite(ref)
         assert fin.sum() > 30
         ref2 = np.array([oracle.lnprob2(p, jup, flux, eflux, bounds, td, tbg) for p in P + 1e-13])
-        ok = fin & (np.abs(ref2 - ref) < 1e-7 * np.maximum(1.0, np.abs(ref)))
+        with np.errstate(invalid="ignore"):
+            ok = fin & (np.abs(ref2 - ref) < 1e-7 * np.maximum(1.0, np.abs(ref))) & (np.abs(ref) < 1e12)
         assert ok.sum() > 0.6 * fin.sum()
         err = np.abs(got[ok] - ref[ok])
         assert (err < np.maximum(ATOL, 1e-9 * np.abs(ref[ok]))).all(), err.max()

