@@ -152,9 +152,8 @@ class StretchSampler:
         self.X = self._local_from_global(p0)
         self.lnp = [self.engine.lnprob(x) for x in self.X]
         for l in self.lnp:
-            if not bool(torch.isfinite(l).all()):
-                # emcee raises "Initial state has a large condition number / lnprob is -inf" equivalents
-                raise ValueError("The initial state has walkers with non-finite log probability")
+            if bool(torch.isnan(l).any()):      # emcee: "Probability function returned NaN"; -inf is allowed
+                raise ValueError("Probability function returned NaN")
 
     # ---- the move -------------------------------------------------------------------------------
     def _half_step(self, half):
