@@ -123,6 +123,8 @@ def main():
     ap.add_argument("--stop", default="pyradex", choices=["pyradex", "radex"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--same", type=int, default=-1, help="debug: every model is a copy of draw #SAME (I-cache experiments)")
+    ap.add_argument("--kernel", type=int, default=0, help="rb_opts.kernel: 0 default, 1 v1 LU, 2 v2 without caching")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -174,6 +176,8 @@ def main():
     nl, nn, npart = mol.nlev, mol.nline, mol.npart
 
     tk, nh2, cd = draw(n, rank)                      # weak scaling: every rank gets its own 2^k draws
+    if args.same >= 0:
+        tk[:], nh2[:], cd[:] = tk[args.same], nh2[args.same], cd[args.same]
     dens = np.zeros((n, npart))
     for p, pid in enumerate(mol.partner_id):
         dens[:, p] = {2: 0.25, 3: 0.75}.get(int(pid), 0.0) * nh2
@@ -185,7 +189,7 @@ def main():
     d_it = torch.empty(n, dtype=torch.int32, device=dev)
     d_st = torch.empty(n, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    opts = _lib.default_opts(stop_rule=stop_rule)
+    opts = _lib.default_opts(stop_rule=stop_rule, kernel=args.kernel)
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
 
@@ -219,6 +223,7 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in ev]
     kern_ms = float(sum(step_ms))
     total_iters, _ = ctx.counters()                   # iterations of the last launch (device-counted)
+    cache_stats = ctx.cache_stats()                   # (cached iterations, captures, invalidations), last launch
     niter_host = d_it.cpu().numpy()
     status_host = d_st.cpu().numpy()
 
@@ -276,9 +281,12 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "models_per_gpu": n, "l2": "256 MiB flush write between timed steps",
-                       "outputs": "xpop,tex,tau,surf,niter,status", "kernel": "k_lvg_solve_v2"},
+                       "outputs": "xpop,tex,tau,surf,niter,status",
+                       "kernel": {0: "k_lvg_solve_v2 (frozen-top caching)", 1: "k_lvg_solve_v1", 2: "k_lvg_solve_v2 (no caching)"}[args.kernel]},
             "iters_per_solve": iters_all / (world * n),
             "matrix_iterations_per_s": iters_all / (ms_per_step * 1e-3),
+            "frac_iterations_cached": cache_stats[0] / max(1, total_iters),
+            "captures_per_solve": cache_stats[1] / n, "invalidations_per_solve": cache_stats[2] / n,
             "frac_at_maxiter": float((status_host & 4).astype(bool).mean()),
             "frac_nonfinite": float((status_host & 8).astype(bool).mean()),
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

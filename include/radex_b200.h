@@ -50,7 +50,8 @@ typedef struct rb_opts {
   int32_t stop_rule;   /* rb_stop_rule                                                    */
   int32_t miniter;     /* 10  (core.py:460-461)                                           */
   int32_t maxiter;     /* 200 (core.py:462-463)                                           */
-  int32_t kernel;      /* 0 = default (fastest validated), 1 = v1 shared-memory pivoted LU */
+  int32_t kernel;      /* 0 = default (fastest validated), 1 = v1 shared-memory pivoted LU,
+                          2 = v2 without frozen-top caching (cross-check / A-B)             */
   double abs_tol;      /* 1e-16 (core.py:857)                                             */
   double fk_epi;       /* h c / k_B used by the brightness epilogue (astropy, core.py:981-984) */
   double thc_epi;      /* 2 h c     used by the brightness epilogue                        */
@@ -141,6 +142,10 @@ int rb_stretch_accept_dev(rb_ctx *ctx, int64_t ns, int32_t ndim, double *S, doub
 /* counters of the last solve/lnprob call on this ctx (device-measured, read back on request):
  * total matrix iterations summed over models, and kernels launched since ctx creation.        */
 int rb_ctx_counters(rb_ctx *ctx, int64_t *total_iters_last, int64_t *launches_total);
+
+/* frozen-top caching statistics of the last solve/lnprob call: stats3[0] matrix iterations that ran
+ * on the cached path, [1] captures, [2] invalidations (a frozen line turned optically thick).  */
+int rb_ctx_cache_stats(rb_ctx *ctx, int64_t *stats3);
 
 /* measured FP64 FMA throughput of this GPU (TFLOP/s), the roofline denominator bench.py reports */
 int rb_fp64_peak(rb_ctx *ctx, double *tflops);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "rb_stretch_accept_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64,
                                         C.c_int32, C.c_int64, C.c_int64, _vp]),
     "rb_ctx_counters": (C.c_int, [_vp, _lp, _lp]),
+    "rb_ctx_cache_stats": (C.c_int, [_vp, _lp]),
     "rb_fp64_peak": (C.c_int, [_vp, _dp]),
 }
 
@@ -196,6 +197,12 @@ class Context:
         v = C.c_double(0.0)
         check(load().rb_fp64_peak(self.handle, C.byref(v)))
         return v.value
+
+    def cache_stats(self):
+        """(cached iterations, captures, invalidations) of the last solve/lnprob call."""
+        a = (C.c_int64 * 3)()
+        check(load().rb_ctx_cache_stats(self.handle, a))
+        return tuple(int(v) for v in a)
 
     def counters(self):
         it, ln = C.c_int64(), C.c_int64()

@@ -59,6 +59,8 @@ struct SolveCfg {
   double deltav_cms, tbg;
   int method, stop_rule, miniter, maxiter;
   double abs_tol, fk_epi, thc_epi;
+  int cache;                    // v2: frozen-top caching enabled (rb_opts.kernel != 2)
+  unsigned long long *stats;    // v2: [0] cached iterations, [1] captures, [2] invalidations
 };
 
 struct rb_ctx {
@@ -640,7 +642,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double *sm = smem + (size_t)wib * v2::SLAB;
-  double *gB = cfg.bslab + ((size_t)blockIdx.x * V2_WARPS + wib) * v2::NB;
+  double *gB = cfg.bslab + ((size_t)blockIdx.x * V2_WARPS + wib) * v2::GSLAB;
   unsigned phase = 0;
   if (lane == 0) v2::mbar_init(sm + v2::O_MBAR, 1);
   __syncwarp();
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lnprob_v2(MolDev mol, Solv
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double *sm = smem + (size_t)wib * v2::SLAB;
-  double *gB = cfg.bslab + ((size_t)blockIdx.x * V2_WARPS + wib) * v2::NB;
+  double *gB = cfg.bslab + ((size_t)blockIdx.x * V2_WARPS + wib) * v2::GSLAB;
   unsigned phase = 0;
   if (lane == 0) v2::mbar_init(sm + v2::O_MBAR, 1);
   __syncwarp();
@@ -885,6 +887,8 @@ SolveCfg make_cfg(const rb_ctx *ctx, const rb_opts *o, double deltav_kms, double
   c.abs_tol = d.abs_tol;
   c.fk_epi = d.fk_epi;
   c.thc_epi = d.thc_epi;
+  c.cache = (d.kernel != 2);
+  c.stats = ctx->counters + 3;
   return c;
 }
 
@@ -926,7 +930,7 @@ Launch v1_launch(rb_ctx *ctx, long long n) {
 
 bool use_v2(const rb_ctx *ctx, const rb_opts *o) {
   const int kernel = o ? o->kernel : 0;
-  return kernel != 1 && ctx->mol.nlev == v2::NL && ctx->mol.nline <= v2::MAXLINE;
+  return kernel != 1 && kernel <= 2 && kernel >= 0 && ctx->mol.nlev == v2::NL && ctx->mol.nline <= v2::MAXLINE;
 }
 
 Launch v2_launch(rb_ctx *ctx, long long n) {
@@ -1056,7 +1060,7 @@ int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess)
-        e = cudaMalloc(&ctx->bslab, (size_t)ctx->sm_count * V2_WARPS * v2::NB * sizeof(double));
+        e = cudaMalloc(&ctx->bslab, (size_t)ctx->sm_count * V2_WARPS * v2::GSLAB * sizeof(double));
     }
     if (e != cudaSuccess) {
       rb_set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
@@ -1359,6 +1363,16 @@ int rb_ctx_counters(rb_ctx *ctx, int64_t *total_iters_last, int64_t *launches_to
   ctx->last_total_iters = (long long)cnt[1];
   if (total_iters_last) *total_iters_last = ctx->last_total_iters;
   if (launches_total) *launches_total = ctx->launches;
+  return RB_OK;
+}
+
+int rb_ctx_cache_stats(rb_ctx *ctx, int64_t *stats3) {
+  if (!ctx || !stats3) return RB_ERR_ARG;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  unsigned long long cnt[3] = {0, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(cnt, ctx->counters + 3, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 3; ++i) stats3[i] = (int64_t)cnt[i];
   return RB_OK;
 }
 
