@@ -98,6 +98,8 @@ def check(rc):
 def default_opts(**kw) -> rb_opts:
     o = rb_opts()
     load().rb_default_opts(C.byref(o))
+    if "RB_KERNEL" in os.environ:       # debugging aid: force a kernel variant (see rb_opts.kernel)
+        o.kernel = int(os.environ["RB_KERNEL"])
     for k, v in kw.items():
         if v is not None:
             setattr(o, k, v)

@@ -657,21 +657,21 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
 #pragma unroll
     for (int p = 0; p < RB_MAXPART; ++p) dens[p] = (p < mol.npart) ? io.dens[idx * mol.npart + p] : 0.0;
     int st = 0;
-    v2::LineRegs L;
-    const int it = v2::solve(mol, sm, gB, phase, lane, io.tkin[idx], dens, io.cdmol[idx], cfg, L, &st);
+    const double cdmol = io.cdmol[idx];
+    const int it = v2::solve(mol, sm, gB, phase, lane, io.tkin[idx], dens, cdmol, cfg, &st);
     const bool bad = (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) != 0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     int nonfinite = 0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int l = lane + 32 * h;
-      if (l < nn) {
-        const double sf = bad ? qnan : v2::surf(L, h, cfg);
-        if (!bad && !isfinite(sf)) nonfinite = 1;
-        if (io.surf) io.surf[idx * nn + l] = sf;
-        if (io.tex) io.tex[idx * nn + l] = bad ? qnan : L.tex[h];
-        if (io.tau) io.tau[idx * nn + l] = bad ? qnan : L.tau[h];
+#pragma unroll 1
+    for (int l = lane; l < nn; l += 32) {
+      double tex = qnan, tau = qnan, sf = qnan;
+      if (!bad) {
+        v2::line_results(mol, sm, l, cdmol, cfg, tex, tau, sf);
+        if (!isfinite(sf)) nonfinite = 1;
       }
+      if (io.surf) io.surf[idx * nn + l] = sf;
+      if (io.tex) io.tex[idx * nn + l] = tex;
+      if (io.tau) io.tau[idx * nn + l] = tau;
     }
     if (io.xpop)
       for (int i = lane; i < nl; i += 32) io.xpop[idx * nl + i] = bad ? qnan : sm[v2::O_X + i];
@@ -722,20 +722,19 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lnprob_v2(MolDev mol, Solv
           dens[q] = (q < mol.npart && mol.part_id[q] == 2) ? (1.0 - fortho) * dens_tot
                     : (q < mol.npart && mol.part_id[q] == 3) ? fortho * dens_tot : 0.0;
         int st = 0;
-        v2::LineRegs L;
-        const int it = v2::solve(mol, sm, gB, phase, lane, pow(10.0, p[4 * c + 1]), dens, pow(10.0, p[4 * c + 2]), cfg, L, &st);
+        const double cdmol = pow(10.0, p[4 * c + 2]);
+        const int it = v2::solve(mol, sm, gB, phase, lane, pow(10.0, p[4 * c + 1]), dens, cdmol, cfg, &st);
         if (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) {
           value_error = true;  // ValueError -> -inf (emcee_radex.py:134-137)
         } else {
           ++solves;
           iters += (unsigned long long)((st & RB_ST_MAXITER) ? it : it + 1);
-          // line fluxes through a small shared staging area (the panel-row buffer is free now)
-          double *stage = sm + v2::O_QROW;
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (L.on[h]) stage[lane + 32 * h] = v2::surf(L, h, cfg);
-          __syncwarp();
-          if (lane < io.obs.nobs) model += stage[io.obs.jup[lane] - 1] * pow(10.0, p[4 * c + 3]) * 1.0e23;
+          // only the observed lines' fluxes are needed: lane i < nobs evaluates line Jup_i - 1
+          if (lane < io.obs.nobs) {
+            double tex, tau, sf;
+            v2::line_results(mol, sm, io.obs.jup[lane] - 1, cdmol, cfg, tex, tau, sf);
+            model += sf * pow(10.0, p[4 * c + 3]) * 1.0e23;
+          }
         }
         __syncwarp();
       }
