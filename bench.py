@@ -123,6 +123,7 @@ def main():
     ap.add_argument("--stop", default="pyradex", choices=["pyradex", "radex"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sort", default="", help="debug: order the models by cd | tk | top (highest thick line, from a first pass)")
     ap.add_argument("--same", type=int, default=-1, help="debug: every model is a copy of draw #SAME (I-cache experiments)")
     ap.add_argument("--kernel", type=int, default=0, help="rb_opts.kernel: 0 default, 1 v1 LU, 2 v2 without caching")
     args = ap.parse_args()
@@ -178,6 +179,9 @@ def main():
     tk, nh2, cd = draw(n, rank)                      # weak scaling: every rank gets its own 2^k draws
     if args.same >= 0:
         tk[:], nh2[:], cd[:] = tk[args.same], nh2[args.same], cd[args.same]
+    if args.sort in ("cd", "tk"):
+        o = np.argsort(cd if args.sort == "cd" else tk, kind="stable")
+        tk, nh2, cd = tk[o].copy(), nh2[o].copy(), cd[o].copy()
     dens = np.zeros((n, npart))
     for p, pid in enumerate(mol.partner_id):
         dens[:, p] = {2: 0.25, 3: 0.75}.get(int(pid), 0.0) * nh2
@@ -203,9 +207,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    if args.sort == "top":      # oracle ordering: by the highest optically thick line of the converged model
+        launch()
+        torch.cuda.synchronize(dev)
+        tau = d_tau.cpu().numpy()
+        thick = np.abs(tau) * 0.5 >= 0.01
+        top = np.where(thick.any(axis=1), thick.shape[1] - 1 - np.argmax(thick[:, ::-1], axis=1), -1)
+        o = np.argsort(top, kind="stable")
+        tk, nh2, cd, dens = tk[o].copy(), nh2[o].copy(), cd[o].copy(), dens[o].copy()
+        d_tk.copy_(torch.from_numpy(tk)); d_cd.copy_(torch.from_numpy(cd)); d_dens.copy_(torch.from_numpy(dens))
     for _ in range(args.warmup):
         launch()
     torch.cuda.synchronize(dev)
+    launches_before = ctx.counters()[1]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -222,7 +236,8 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     kern_ms = float(sum(step_ms))
-    total_iters, _ = ctx.counters()                   # iterations of the last launch (device-counted)
+    total_iters, launches_after = ctx.counters()      # iterations of the last step (device-counted)
+    launches_timed = launches_after - launches_before  # kernels launched inside the kernel-only timed region
     cache_stats = ctx.cache_stats()                   # (cached iterations, captures, invalidations), last launch
     niter_host = d_it.cpu().numpy()
     status_host = d_st.cpu().numpy()
@@ -282,7 +297,9 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "models_per_gpu": n, "l2": "256 MiB flush write between timed steps",
                        "outputs": "xpop,tex,tau,surf,niter,status",
-                       "kernel": {0: "k_lvg_solve_v2 (frozen-top caching)", 1: "k_lvg_solve_v1", 2: "k_lvg_solve_v2 (no caching)"}[args.kernel]},
+                       "kernel": {0: "k_lvg_solve_v2 (frozen-top caching, two launches ordered by lead-block size)",
+                                  1: "k_lvg_solve_v1", 2: "k_lvg_solve_v2 (no caching)",
+                                  3: "k_lvg_solve_v2 (frozen-top caching, single launch)"}[args.kernel]},
             "iters_per_solve": iters_all / (world * n),
             "matrix_iterations_per_s": iters_all / (ms_per_step * 1e-3),
             "frac_iterations_cached": cache_stats[0] / max(1, total_iters),
@@ -290,7 +307,7 @@ def main():
             "frac_at_maxiter": float((status_host & 4).astype(bool).mean()),
             "frac_nonfinite": float((status_host & 8).astype(bool).mean()),
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": args.steps,
+            "gpu_launches": launches_timed,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": None,
                          "peak_source": "rb_fp64_peak DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 "

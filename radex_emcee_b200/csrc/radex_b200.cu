@@ -60,6 +60,7 @@ struct SolveCfg {
   int method, stop_rule, miniter, maxiter;
   double abs_tol, fk_epi, thc_epi;
   int cache;                    // v2: frozen-top caching enabled (rb_opts.kernel != 2)
+  int sched;                    // v2: two-launch scheduling allowed (rb_opts.kernel == 0)
   unsigned long long *stats;    // v2: [0] cached iterations, [1] captures, [2] invalidations
 };
 
@@ -75,7 +76,10 @@ struct rb_ctx {
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
   unsigned long long *counters = nullptr; // [0] work queue head, [1] total iterations, [2] solves
-  double *bslab = nullptr;                // v2: sm_count x V2_WARPS x NB doubles
+  double *bslab = nullptr;                // v2: sm_count x V2_WARPS x GSLAB doubles
+  void *sched_buf = nullptr;              // v2 scheduling: parked state, keys, order (grow-only)
+  size_t sched_bytes = 0;
+  unsigned long long *sched_small = nullptr;   // 64 words: histogram, offsets, cursors, parked count
   long long launches = 0;
   long long last_total_iters = 0;
 };
@@ -465,6 +469,13 @@ struct SolveIO {
   double *xpop, *tex, *tau, *surf;
   int *niter, *status;
   unsigned long long *counters;
+  // v2 two-launch scheduling (lvg_v2.cuh): 0 single launch; 1 = launch A (run to the engine choice, park);
+  // 2 = launch B (resume the parked models in the order given)
+  int sched;
+  double *state;                       // n x v2::STATE_STRIDE
+  int *keys;                           // n: Kp wanted by a parked model, -1 = finished in launch A
+  const int *order;                    // launch B: model index of queue position q
+  const unsigned long long *n_parked;  // launch B: number of parked models (device)
 };
 
 __global__ void __launch_bounds__(256) k_lvg_solve_v1(MolDev mol, SolveCfg cfg, SolveIO io) {
@@ -637,6 +648,7 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
 // v2 kernels (41-level molecules): register-resident GTH elimination with DMMA updates
 // ------------------------------------------------------------------------------------------------
 #define V2_WARPS 12
+#define RB_SCHED_MIN 8192   // batches smaller than this run as one launch
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, SolveCfg cfg, SolveIO io) {
   extern __shared__ double smem[];
@@ -648,17 +660,26 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
   __syncwarp();
   const int nl = mol.nlev, nn = mol.nline;
   unsigned long long iters = 0;
+  const long long limit = (io.sched == 2) ? (long long)*io.n_parked : io.n;
   for (;;) {
     unsigned long long idx = 0;
     if (lane == 0) idx = atomicAdd(&io.counters[0], 1ULL);
     idx = __shfl_sync(0xffffffffu, idx, 0);
-    if ((long long)idx >= io.n) break;
+    if ((long long)idx >= limit) break;
+    if (io.sched == 2) idx = (unsigned long long)io.order[idx];
     double dens[RB_MAXPART];
 #pragma unroll
     for (int p = 0; p < RB_MAXPART; ++p) dens[p] = (p < mol.npart) ? io.dens[idx * mol.npart + p] : 0.0;
-    int st = 0;
+    int st = 0, key = -1;
     const double cdmol = io.cdmol[idx];
-    const int it = v2::solve(mol, sm, gB, phase, lane, io.tkin[idx], dens, cdmol, cfg, &st);
+    const int it = v2::solve(mol, sm, gB, phase, lane, io.tkin[idx], dens, cdmol, cfg, &st, io.sched,
+                             io.state ? io.state + idx * v2::STATE_STRIDE : nullptr, &key);
+    if (io.sched == 1 && lane == 0) io.keys[idx] = (st & v2::ST_PARKED) ? key : -1;
+    if (st & v2::ST_PARKED) {   // launch B finishes this model
+      iters += (unsigned long long)it;
+      __syncwarp();
+      continue;
+    }
     const bool bad = (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) != 0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     int nonfinite = 0;
@@ -681,10 +702,41 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
       if (io.niter) io.niter[idx] = it;
       if (io.status) io.status[idx] = st;
     }
-    iters += bad ? 0 : (unsigned long long)((st & RB_ST_MAXITER) ? it : it + 1);
+    // calls of matrix() made here; launch A already counted the first IT_DECIDE of a resumed model
+    iters += bad ? 0 : (unsigned long long)(((st & RB_ST_MAXITER) ? it : it + 1) - (io.sched == 2 ? v2::IT_DECIDE : 0));
     __syncwarp();
   }
   if (lane == 0 && iters) atomicAdd(&io.counters[1], iters);
+}
+
+// ---- ordering of the parked models between the two launches: counting sort by key, heaviest first ------
+constexpr int SCHED_NKEY = 16;
+// small[0..15] histogram, [16..31] bin offsets, [32..47] bin cursors, [48] number of parked models
+__global__ void k_sched_hist(const int *keys, long long n, unsigned long long *small) {
+  __shared__ unsigned int h[SCHED_NKEY];
+  if (threadIdx.x < SCHED_NKEY) h[threadIdx.x] = 0;
+  __syncthreads();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n && keys[i] >= 0) atomicAdd(&h[keys[i] & (SCHED_NKEY - 1)], 1u);
+  __syncthreads();
+  if (threadIdx.x < SCHED_NKEY && h[threadIdx.x]) atomicAdd(&small[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+__global__ void k_sched_scan(unsigned long long *small) {
+  unsigned long long off = 0;
+  for (int k = SCHED_NKEY - 1; k >= 0; --k) {   // heaviest key first: the tail of launch B is made of light models
+    small[16 + k] = off;
+    small[32 + k] = 0;
+    off += small[k];
+  }
+  small[48] = off;
+}
+__global__ void k_sched_scatter(const int *keys, long long n, unsigned long long *small, int *order) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n && keys[i] >= 0) {
+    const int k = keys[i] & (SCHED_NKEY - 1);
+    const unsigned long long pos = atomicAdd(&small[32 + k], 1ULL);
+    order[small[16 + k] + pos] = (int)i;
+  }
 }
 
 template <int NCOMP>
@@ -887,6 +939,7 @@ SolveCfg make_cfg(const rb_ctx *ctx, const rb_opts *o, double deltav_kms, double
   c.fk_epi = d.fk_epi;
   c.thc_epi = d.thc_epi;
   c.cache = (d.kernel != 2);
+  c.sched = (d.kernel == 0);
   c.stats = ctx->counters + 3;
   return c;
 }
@@ -929,7 +982,7 @@ Launch v1_launch(rb_ctx *ctx, long long n) {
 
 bool use_v2(const rb_ctx *ctx, const rb_opts *o) {
   const int kernel = o ? o->kernel : 0;
-  return kernel != 1 && kernel <= 2 && kernel >= 0 && ctx->mol.nlev == v2::NL && ctx->mol.nline <= v2::MAXLINE;
+  return kernel != 1 && kernel <= 3 && kernel >= 0 && ctx->mol.nlev == v2::NL && ctx->mol.nline <= v2::MAXLINE;
 }
 
 Launch v2_launch(rb_ctx *ctx, long long n) {
@@ -1081,6 +1134,8 @@ void rb_ctx_destroy(rb_ctx *ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->counters) cudaFree(ctx->counters);
   if (ctx->bslab) cudaFree(ctx->bslab);
+  if (ctx->sched_buf) cudaFree(ctx->sched_buf);
+  if (ctx->sched_small) cudaFree(ctx->sched_small);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1116,10 +1171,39 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
   CUDA_TRY(cudaSetDevice(ctx->device));
   const SolveCfg cfg = make_cfg(ctx, opts, deltav_kms, tbg, geometry);
   CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-  SolveIO io{n, tkin, dens, cdmol, xpop, tex, tau, surf, niter, status, ctx->counters};
+  SolveIO io{n, tkin, dens, cdmol, xpop, tex, tau, surf, niter, status, ctx->counters, 0, nullptr, nullptr, nullptr, nullptr};
   if (use_v2(ctx, opts)) {
     const Launch L = v2_launch(ctx, n);
-    k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+    if (cfg.sched && cfg.cache && geometry == RB_GEOM_LVG && n >= RB_SCHED_MIN) {
+      // two launches with the parked models ordered by the lead-block size they will run with (lvg_v2.cuh)
+      const size_t b_state = align256((size_t)n * v2::STATE_STRIDE * sizeof(double)), b_int = align256((size_t)n * sizeof(int));
+      if (b_state + 2 * b_int > ctx->sched_bytes) {
+        if (ctx->sched_buf) cudaFree(ctx->sched_buf);
+        ctx->sched_buf = nullptr;
+        ctx->sched_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->sched_buf, b_state + 2 * b_int));
+        ctx->sched_bytes = b_state + 2 * b_int;
+      }
+      if (!ctx->sched_small) CUDA_TRY(cudaMalloc(&ctx->sched_small, 64 * sizeof(unsigned long long)));
+      io.state = static_cast<double *>(ctx->sched_buf);
+      io.keys = reinterpret_cast<int *>(static_cast<char *>(ctx->sched_buf) + b_state);
+      int *order = reinterpret_cast<int *>(static_cast<char *>(ctx->sched_buf) + b_state + b_int);
+      CUDA_TRY(cudaMemsetAsync(ctx->sched_small, 0, 64 * sizeof(unsigned long long), ctx->stream));
+      io.sched = 1;
+      k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+      const int tpb = 256, nb = (int)((n + tpb - 1) / tpb);
+      k_sched_hist<<<nb, tpb, 0, ctx->stream>>>(io.keys, n, ctx->sched_small);
+      k_sched_scan<<<1, 1, 0, ctx->stream>>>(ctx->sched_small);
+      k_sched_scatter<<<nb, tpb, 0, ctx->stream>>>(io.keys, n, ctx->sched_small, order);
+      CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));   // queue head only
+      io.sched = 2;
+      io.order = order;
+      io.n_parked = ctx->sched_small + 48;
+      k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+      ctx->launches += 4;
+    } else {
+      k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+    }
   } else {
     const Launch L = v1_launch(ctx, n);
     k_lvg_solve_v1<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);

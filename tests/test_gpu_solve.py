@@ -226,6 +226,23 @@ def test_frozen_top_cache_matches_full_elimination(ctx):
         assert ((a["status"] ^ b["status"])[sel] & 8 == 0).all()
 
 
+def test_two_launch_schedule_is_bit_identical(ctx):
+    """Large batches run as two launches with the models re-ordered in between (kernel=0); the arithmetic
+    per model is the same as in the single launch (kernel=3), so every output must match bit for bit,
+    including with a cap below / at the parking point and with out-of-range models in the batch."""
+    P = draw_params(np.random.default_rng(33), 20000, 10.926)
+    P[5, 0] = -1.0          # T out of range
+    P[77, 2] = 1e30         # N out of range
+    for kw in ({}, {"maxiter": 2}, {"maxiter": 1}, {"maxiter": 3}, {"stop_rule": _lib.STOP_RADEX}):
+        a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, **kw)
+        ita, _ = ctx.counters()
+        b = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, kernel=3, **kw)
+        itb, _ = ctx.counters()
+        assert ita == itb, (kw, ita, itb)
+        for k in ("xpop", "tex", "tau", "surf", "niter", "status"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg="%s %s" % (k, kw))
+
+
 def test_determinism(ctx):
     P = draw_params(np.random.default_rng(9), 200, 10.926)
     a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926)

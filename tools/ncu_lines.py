@@ -61,3 +61,28 @@ print('%6s %6s %5s  %s' % ('samp%', 'inst%', 'sass', 'location'))
 for (f, ln), (i, s, c, st) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:topn]:
     top = ' '.join('%s=%.0f%%' % (k, 100 * v / max(1, s)) for k, v in st.most_common(3))
     print('%5.1f%% %5.1f%% %5d  %s:%d  %s   [%s]' % (100 * s / tot_s, 100 * i / tot_i, c, f, ln, text(f, ln), top))
+
+# ---- coarse regions: functions of lvg_v2.cuh, and inside solve() the blocks introduced by "// ----" comments
+src = srccache.get('lvg_v2.cuh') or (open(glob.glob('/root/repo/radex_emcee_b200/csrc/lvg_v2.cuh')[0]).read().split('\n'))
+marks = []
+for i, t in enumerate(src, 1):
+    st = t.strip()
+    if st.startswith('__device__') or st.startswith('template <') and False:
+        m = re.search(r'(\w+)\s*\(', st.split('__forceinline__')[-1].split('__noinline__')[-1])
+        marks.append((i, m.group(1) if m else st[:30]))
+    elif st.startswith('// ----') and marks and marks[-1][1].startswith('solve'):
+        marks.append((i, 'solve: ' + st[7:60].strip(' -')))
+reg = collections.defaultdict(lambda: [0.0, 0.0])
+for (f, ln), (i, s_, c, st) in agg.items():
+    name = f
+    if f == 'lvg_v2.cuh':
+        name = 'lvg_v2.cuh:?'
+        for a, nm in marks:
+            if a <= ln:
+                name = nm
+    reg[name][0] += i
+    reg[name][1] += s_
+print('\nregions (inst%, samp%):')
+for nm, (i, s_) in sorted(reg.items(), key=lambda kv: -kv[1][1]):
+    if s_ / tot_s > 0.002:
+        print('%5.1f%% %5.1f%%  %s' % (100 * i / tot_i, 100 * s_ / tot_s, nm))
