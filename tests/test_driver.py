@@ -1,0 +1,84 @@
+"""Host logic of the per-source pipeline (driver.py): finite-difference batching, summaries; and, on a GPU,
+one short end-to-end fit (reference: main() of emcee/emcee_radex.py:382-531, emcee_radex_2comp.py:479-608)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from radex_emcee_b200 import driver
+from radex_emcee_b200.data import DATA_DIR, read_data
+
+
+def test_forward_steps_follow_scipy_two_point_rule():
+    from scipy.optimize._numdiff import approx_derivative
+    lo, hi = np.array([0.0, -5.0, 1.0]), np.array([2.0, 5.0, 3.0])
+    x = np.array([2.0, -1.5, 1.0])                # first at its upper bound, last at its lower bound
+    h = driver.forward_steps(x, lo, hi)
+    assert h[0] < 0 and h[1] < 0 and h[2] > 0     # flipped at the upper bound; sign(x) elsewhere
+    assert np.all((x + h >= lo) & (x + h <= hi))
+    f = lambda p: np.array([p[0] ** 2 + p[1], np.sin(p[2]) * p[0], p[1] * p[2]])
+    fb = lambda P: np.array([f(p) for p in np.atleast_2d(P)])
+    J = driver.fd_jacobian(fb, x, lo, hi)
+    Jref = approx_derivative(f, x, method="2-point", bounds=(lo, hi))
+    np.testing.assert_allclose(J, Jref, rtol=0, atol=1e-12)
+
+
+def test_value_and_gradient_is_one_batched_call():
+    calls = []
+
+    def fun(P):
+        calls.append(np.array(P))
+        return np.sum(np.asarray(P) ** 2, axis=1)
+
+    x = np.array([1.0, -2.0, 0.5, 3.0])
+    f, g = driver.fd_value_and_gradient(fun, x, np.full(4, -10.0), np.array([10.0, 10.0, 10.0, 3.0]))
+    assert len(calls) == 1 and calls[0].shape == (5, 4)
+    assert f == pytest.approx(14.25)
+    np.testing.assert_allclose(g, 2 * x, atol=1e-6)
+    assert calls[0][4, 3] < 3.0                  # at the upper bound the step goes inwards
+
+
+def test_summaries():
+    rng = np.random.default_rng(0)
+    chain = rng.normal([4.0, 1.5, 17.0, -10.0, 3.0, 2.5, 16.0, -11.0], 0.1, size=(20000, 8))
+    s = driver.posterior_summary(chain, 2)
+    assert len(s) == 2 and set(s[0]) == {"n_H2", "T_kin", "N_CO/dv", "P"}
+    med, up, dn = s[0]["P"]
+    assert med == pytest.approx(5.5, abs=0.01) and up == pytest.approx(0.1 * np.sqrt(2), rel=0.05)
+    assert s[1]["n_H2"][0] == pytest.approx(3.0, abs=0.01)
+    X = rng.normal(size=(500, 3)) * [1.0, 10.0, 0.1]
+    for metric in ("mahalanobis", "z", "euclidean"):
+        x, i, d2 = driver.nearest_sample_to_vector(X, X[17] + 1e-9, metric=metric)
+        assert i == 17 and d2 < 1e-10 and np.array_equal(x, X[17])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ncomp", [1, 2])
+def test_fit_source_end_to_end(tmp_path, ncomp):
+    data = read_data(os.path.join(DATA_DIR, "flux.dat" if ncomp == 1 else "flux_for2p.dat"))
+    res = driver.fit_source("G09v1.97", data, ncomp=ncomp, nwalkers=64, n_iter_burn=10, n_iter_walk=20,
+                            outdir=str(tmp_path))
+    b = res["bounds"]
+    assert np.all((res["popt"] >= b[:, 0]) & (res["popt"] <= b[:, 1]))
+    assert np.all((res["pmin"] >= b[:, 0]) & (res["pmin"] <= b[:, 1]))
+    assert res["chain"].shape == (20, 64, 4 * ncomp) and res["lnprobability"].shape == (20, 64)
+    assert np.isfinite(res["lnprobability"]).mean() > 0.9 and 0.05 < res["acceptance_fraction"] < 0.95
+    # curve_fit improved on the starting point: chi^2 of the SLED at popt is below the one at p0
+    mod = driver._modules(ncomp)
+    from radex_emcee_b200.radex import Radex
+    tbg, _ra, bounds, p0 = mod.source_setup(res["z"])
+    R = Radex(species="co", density={"oH2": 7.5e9, "pH2": 2.5e9}, column=1e6, temperature=20.0, tbackground=tbg)
+    Jup, flux, eflux = res["data"]
+    chi2 = lambda p: float(np.sum(((flux - mod.model_lvg(Jup, p, R)) / eflux) ** 2))
+    assert chi2(res["popt"]) <= chi2(p0) + 1e-9
+    # the batched gradients cost one launch per iteration, not ndim + 1
+    assert res["prefit_info"]["lnprob_launches"] < 400
+    with open(res["pickle"], "rb") as f:
+        tup = pickle.load(f)
+    assert len(tup) == (8 if ncomp == 1 else 9) and tup[0] == "G09v1.97"
+    np.testing.assert_array_equal(tup[-1][0], res["chain"])
+    import io
+    buf = io.StringIO()
+    driver.print_summary(res, ncomp, file=buf)
+    assert buf.getvalue().count("xxx:") >= 7
