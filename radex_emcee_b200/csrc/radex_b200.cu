@@ -43,6 +43,7 @@
 // ------------------------------------------------------------------------------------------------
 struct MolDev {
   int nlev, nline, npart;
+  int sorted_levels;                      // eterm strictly increasing (true for LAMDA files)
   const double *eterm, *gstat;            // [nlev]
   const int *iupp, *ilow;                 // [nline] 0-based
   const double *aeinst, *xnu;             // [nline]
@@ -1066,6 +1067,9 @@ int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
   m.nlev = mol->nlev;
   m.nline = mol->nline;
   m.npart = mol->npart;
+  m.sorted_levels = 1;
+  for (int i = 0; i + 1 < mol->nlev; ++i)
+    if (!(mol->eterm[i + 1] > mol->eterm[i])) m.sorted_levels = 0;
   int rc = RB_OK;
 #define UP(vec, dst)                                  \
   if (rc == RB_OK) rc = upload(ctx, vec, &dst);
