@@ -1,0 +1,150 @@
+// lvg_small.cuh -- the cached engine of lvg_v2.cuh for SMALL lead blocks, one HALF-WARP per model.
+//
+// In the forward sweep three quarters of the models keep every optically thick line below level 16, so
+// their cached iterations (lvg_v2.cuh: CACHED) eliminate a lead block of n = 12 or 16 levels with one row
+// per lane -- half of the warp idles, and the slab that has to stay on chip for them is 8.8 KB, not 19 KB.
+// This kernel runs those models two per warp (lanes 0-15 / 16-31, each half with its own slab and its own
+// iteration state), 24 models per SM instead of 12.  It contains NO full elimination: launch B captures the
+// frozen top of such a model and parks lead block, response matrix and line bases (EXT_STRIDE doubles);
+// a model whose frozen lines turn thick is parked again and finished by launch C (v2::solve, sched = 4).
+//
+// Per model the arithmetic is the one of v2::lead_solve and of the iteration loop of v2::solve, operation
+// for operation and in the same association (the 32-lane butterflies are reproduced as "pair, then 16-lane
+// butterfly"), so the results are bit-identical to the single-launch path
+// (tests/test_gpu_solve.py::test_two_launch_schedule_is_bit_identical).
+//
+// What it replaces: the calls 2.. of matrix() + lubksb (emcee/pyradex/radex/radex.so@0x17f70, 0x17cb0) made
+// by run_radex's loop (emcee/pyradex/core.py:856-925) for these models.
+#pragma once
+
+namespace v2s {
+
+using v2::LDB;
+using v2::NL;
+using v2::ld2;
+using v2::st2;
+
+using v2::KP_SMALL_MAX;               // lead blocks of 12 and 16 levels
+using v2::EXT_LEAD;
+using v2::EXT_STRIDE;
+constexpr int NROW_S = 4 * KP_SMALL_MAX;
+// ---- per-model shared-memory slab (doubles) ------------------------------------------------------------
+constexpr int S_LEAD = 0;            // lead block, row pitch n + 2                      (<= 16 x 18)
+constexpr int S_M = 288;             // M[i][f]: frozen populations from the lead ones, pitch 42 - n (<= 12 x 30, 16 x 26)
+constexpr int S_PB = S_M + 416;      // pivot-row broadcast buffers, 2 x 16 (1/s_k rides in slot K)
+constexpr int S_VT = S_PB + 32;      // raw pivot columns, triangular                    (<= 120)
+constexpr int S_X = S_VT + 120;      // relaxed populations
+constexpr int S_XNEW = S_X + 42;     // un-relaxed populations of this call
+constexpr int S_BETA = S_XNEW + 42;  // per line: escape probability of the call about to be made
+constexpr int S_DNB = S_BETA + 40;   //           non-radiative part of q[m][n] (collisions + Schur term)
+constexpr int S_UPB = S_DNB + 40;    //           non-radiative part of q[n][m]
+constexpr int S_TEX = S_UPB + 40;    //           excitation temperature
+constexpr int SSLAB = S_TEX + 40;    // 1100 doubles = 8800 B
+static_assert(SSLAB % 2 == 0, "slabs must stay 16 B aligned");
+// ---- per-CTA constants (the same for every model of a call) --------------------------------------------
+constexpr int C_LA = 0, C_LGR = 40, C_LTDEN = 80, C_LECOEF = 120, C_LFKXNU = 160, C_LMN = 200, CSLAB = 220;
+// parked capture (global, per model; v2::EXT_STRIDE = 784 doubles): DNB[40] UPB[40] lead[n(n+2)] M[n(42-n)]
+static_assert(12 * 30 <= 416 && 16 * 26 <= 416, "response matrix overflows its region");
+
+__device__ __forceinline__ double half_sum(double v) {   // butterfly over the 16 lanes of a half-warp
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int half_sum_int(int v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int half_max_int(int v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <int LO, int HI>
+__device__ __forceinline__ double sum_range(const double (&q)[NROW_S]) {   // same association as v2::sum_range
+  if constexpr (HI - LO == 1) {
+    return q[LO];
+  } else {
+    constexpr int MID = (LO + HI) / 2;
+    return sum_range<LO, MID>(q) + sum_range<MID, HI>(q);
+  }
+}
+
+// v2::lead_pivots with hl = lane within the half; both halves run the same pivot on their own block.
+template <int K, int LO>
+__device__ __forceinline__ void lead_pivots(double (&q)[NROW_S], double &rmine, double *pbase, double *vt,
+                                            const int hl) {
+  if constexpr (K >= LO) {
+    const double s = sum_range<0, K>(q);
+    const double rr = v2::rcp1(s);
+    const double r = (s > 0.0) ? rr : 0.0;
+    double *pb = pbase + (K & 1) * 16;
+    if (hl == K) {
+      rmine = r;
+#pragma unroll
+      for (int j = 0; j + 1 < K; j += 2) st2(pb + j, q[j], q[j + 1]);
+      if (K & 1) pb[K - 1] = q[K - 1];
+      pb[K] = r;
+    }
+    __syncwarp();
+    const double w = q[K];
+    if (hl < K) vt[K * (K - 1) / 2 + hl] = w;
+    const double wv = w * pb[K];
+#pragma unroll
+    for (int j = 0; j < K; j += 2) {
+      const double2 u = ld2(pb + j);
+      q[j] = fma(wv, u.x, q[j]);
+      if (j + 1 < K) q[j + 1] = fma(wv, u.y, q[j + 1]);
+    }
+    lead_pivots<K - 1, LO>(q, rmine, pbase, vt, hl);
+  }
+}
+
+// v2::lead_solve for a half-warp; Kp (3 or 4) is the same in both halves of the warp.
+__device__ __forceinline__ double lead_solve(double *sm, const int Kp, const int hl) {
+  const int n = 4 * Kp;
+  double *B = sm + S_LEAD;
+  double q[NROW_S];
+  {
+    const double *row = B + ((hl < n) ? hl : 0) * (n + 2);
+#pragma unroll
+    for (int j = 0; j < NROW_S; j += 4) {
+      if (j >= n) break;
+      const double2 a = ld2(row + j), b = ld2(row + j + 2);
+      q[j] = a.x; q[j + 1] = a.y; q[j + 2] = b.x; q[j + 3] = b.y;
+    }
+  }
+  double rmine = 0.0;
+  double *pbase = sm + S_PB, *vtb = sm + S_VT;
+  switch (Kp) {
+    case 4: lead_pivots<15, 12>(q, rmine, pbase, vtb, hl); [[fallthrough]];
+    default: lead_pivots<11, 1>(q, rmine, pbase, vtb, hl);
+  }
+  __syncwarp();   // Vt complete
+  const int nf = NL - n, pitch = LDB - n;   // 29 or 25 frozen levels: lane hl owns n + hl and n + 16 + hl
+  const double *vt = vtb + hl * (hl - 1) / 2;
+  const bool two = hl + 16 < nf;
+  const double *Mc1 = sm + S_M + hl, *Mc2 = sm + S_M + (two ? hl + 16 : 0);
+  double Y = 0.0, F1 = 0.0, F2 = 0.0, xi = 1.0, psum = 1.0, xmine = 1.0;
+#pragma unroll
+  for (int i = 0; i < NROW_S - 1; ++i) {
+    if (i >= n - 1) break;
+    Y = fma(xi, vt[i], Y);
+    F1 = fma(xi, Mc1[i * pitch], F1);
+    F2 = fma(xi, Mc2[i * pitch], F2);
+    xi = __shfl_sync(0xffffffffu, rmine * Y, i + 1, 16);
+    psum += xi;
+    xmine = (hl == i + 1) ? xi : xmine;
+  }
+  F1 = fma(xi, Mc1[(n - 1) * pitch], F1);
+  F2 = fma(xi, Mc2[(n - 1) * pitch], F2);
+  if (hl < n) sm[S_XNEW + hl] = xmine;
+  sm[S_XNEW + n + hl] = F1;
+  if (two) sm[S_XNEW + n + 16 + hl] = F2;
+  // v2: psum + warp_sum(lane < nf ? F : 0): the first butterfly step pairs lane l with l + 16
+  return psum + half_sum(F1 + (two ? F2 : 0.0));
+}
+
+}  // namespace v2s

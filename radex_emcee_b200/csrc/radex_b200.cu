@@ -61,7 +61,8 @@ struct SolveCfg {
   int method, stop_rule, miniter, maxiter;
   double abs_tol, fk_epi, thc_epi;
   int cache;                    // v2: frozen-top caching enabled (rb_opts.kernel != 2)
-  int sched;                    // v2: two-launch scheduling allowed (rb_opts.kernel == 0)
+  int sched;                    // v2: two-launch scheduling allowed (rb_opts.kernel == 0 or 4)
+  int small;                    // v2: half-warp engine for lead blocks <= 16 levels (lvg_small.cuh)
   unsigned long long *stats;    // v2: [0] cached iterations, [1] captures, [2] invalidations
 };
 
@@ -463,6 +464,7 @@ __device__ __forceinline__ double rb_surf(const MolDev &mol, const WarpMem &w, i
 }
 
 #include "lvg_v2.cuh"
+#include "lvg_small.cuh"
 
 struct SolveIO {
   long long n;
@@ -477,6 +479,11 @@ struct SolveIO {
   int *keys;                           // n: Kp wanted by a parked model, -1 = finished in launch A
   const int *order;                    // launch B: model index of queue position q
   const unsigned long long *n_parked;  // launch B: number of parked models (device)
+  // half-warp engine (lvg_small.cuh): launch B parks the captures of small-lead models in ext, k_lvg_small runs
+  // them and appends the ones whose frozen lines turn thick to order_c for launch C (sched = 4)
+  double *ext;                         // n x v2s::EXT_STRIDE
+  unsigned long long *sched_small;     // [16+k] first queue position of key k, [48] parked, [49] models for launch C
+  int *order_c;
 };
 
 __global__ void __launch_bounds__(256) k_lvg_solve_v1(MolDev mol, SolveCfg cfg, SolveIO io) {
@@ -661,20 +668,21 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
   __syncwarp();
   const int nl = mol.nlev, nn = mol.nline;
   unsigned long long iters = 0;
-  const long long limit = (io.sched == 2) ? (long long)*io.n_parked : io.n;
+  const long long limit = (io.sched >= 2) ? (long long)*io.n_parked : io.n;
   for (;;) {
     unsigned long long idx = 0;
     if (lane == 0) idx = atomicAdd(&io.counters[0], 1ULL);
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if ((long long)idx >= limit) break;
-    if (io.sched == 2) idx = (unsigned long long)io.order[idx];
+    if (io.sched >= 2) idx = (unsigned long long)io.order[idx];
     double dens[RB_MAXPART];
 #pragma unroll
     for (int p = 0; p < RB_MAXPART; ++p) dens[p] = (p < mol.npart) ? io.dens[idx * mol.npart + p] : 0.0;
     int st = 0, key = -1;
     const double cdmol = io.cdmol[idx];
     const int it = v2::solve(mol, sm, gB, phase, lane, io.tkin[idx], dens, cdmol, cfg, &st, io.sched,
-                             io.state ? io.state + idx * v2::STATE_STRIDE : nullptr, &key);
+                             io.state ? io.state + idx * v2::STATE_STRIDE : nullptr, &key,
+                             (io.sched == 2 && io.ext) ? io.ext + idx * v2::EXT_STRIDE : nullptr);
     if (io.sched == 1 && lane == 0) io.keys[idx] = (st & v2::ST_PARKED) ? key : -1;
     if (st & v2::ST_PARKED) {   // launch B finishes this model
       iters += (unsigned long long)it;
@@ -704,7 +712,9 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
       if (io.status) io.status[idx] = st;
     }
     // calls of matrix() made here; launch A already counted the first IT_DECIDE of a resumed model
-    iters += bad ? 0 : (unsigned long long)(((st & RB_ST_MAXITER) ? it : it + 1) - (io.sched == 2 ? v2::IT_DECIDE : 0));
+    int it_before = (io.sched == 2) ? v2::IT_DECIDE : 0;   // calls counted by the launches that ran them
+    if (io.sched == 4) it_before = (int)(reinterpret_cast<const long long *>(io.state + idx * v2::STATE_STRIDE)[123] & 0xffff);
+    iters += bad ? 0 : (unsigned long long)(((st & RB_ST_MAXITER) ? it : it + 1) - it_before);
     __syncwarp();
   }
   if (lane == 0 && iters) atomicAdd(&io.counters[1], iters);
@@ -737,6 +747,265 @@ __global__ void k_sched_scatter(const int *keys, long long n, unsigned long long
     const int k = keys[i] & (SCHED_NKEY - 1);
     const unsigned long long pos = atomicAdd(&small[32 + k], 1ULL);
     order[small[16 + k] + pos] = (int)i;
+  }
+}
+
+
+// ---- half-warp engine for small lead blocks (lvg_small.cuh): two models per warp, 24 per SM -----------------
+#ifndef VS_WARPS
+#define VS_WARPS 13
+#endif
+
+__global__ void __launch_bounds__(VS_WARPS * 32, 1) k_lvg_small(MolDev mol, SolveCfg cfg, SolveIO io) {
+  using namespace v2s;
+  extern __shared__ double smem[];
+  double *cs = smem;   // per-line constants of this call, shared by the CTA
+  const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4, wib = threadIdx.x >> 5;
+  const unsigned hmask = 0xffffu << (16 * half);
+  double *sm = smem + CSLAB + (size_t)(2 * wib + half) * SSLAB;
+  int *lmn = reinterpret_cast<int *>(cs + C_LMN);
+  const int nl = mol.nlev, nn = mol.nline;
+  // the same expressions as the per-line set-up of v2::solve
+  for (int l = threadIdx.x; l < nn; l += blockDim.x) {
+    const int m = mol.iupp[l], n = mol.ilow[l];
+    const double a = mol.aeinst[l], xnu = mol.xnu[l];
+    const double xt = xnu * xnu * xnu;
+    const double hnu = RB_FK * xnu / cfg.tbg;
+    const double bi = (hnu >= 160.0) ? 1.0e-30 : RB_THC * xt / (exp(hnu) - 1.0);
+    lmn[l] = m | (n << 8);
+    cs[C_LA + l] = a;
+    cs[C_LGR + l] = mol.gstat[m] / mol.gstat[n];
+    cs[C_LTDEN + l] = 1.0 / (RB_FGAUS * xt / a);
+    cs[C_LECOEF + l] = bi / (RB_THC * xt);
+    cs[C_LFKXNU + l] = RB_FK * xnu;
+  }
+  // a slab that never receives a model still runs the arithmetic of its warp: give it finite numbers
+  for (int e = hl; e < SSLAB; e += 16) sm[e] = 1.0;
+  __syncthreads();
+  // queue: positions [first of key 4, parked) of the sorted order; key 4 comes first, then key 3
+  const unsigned long long p_begin = io.sched_small[16 + 4], p3 = io.sched_small[16 + 3], p_end = io.sched_small[48];
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+  bool active = false, pending = false, exhausted = false;
+  long long idx = 0, pidx = 0;
+  int Kp = 0, pKp = 0, it = 0, nthick = 0, topthick = -1;
+  unsigned flags = 0;   // bit t: line hl + 16 t had tau > 0.01f after the last call (RADEX's own stop rule)
+  double cdmol = 1.0, cddv = 1.0;
+  unsigned long long iters = 0, n_cached = 0, n_models = 0, n_inval = 0;
+  for (;;) {
+    // ---- a free half takes the next model of the queue; it starts once its partner runs the same lead size --
+    if (!active && !pending && !exhausted) {
+      unsigned long long t = 0;
+      if (hl == 0) t = atomicAdd(&io.counters[0], 1ULL);
+      t = __shfl_sync(hmask, t, 0, 16);
+      const unsigned long long pos = p_begin + t;
+      if (pos >= p_end) {
+        exhausted = true;
+      } else {
+        pending = true;
+        pidx = io.order[pos];
+        pKp = (pos < p3) ? 4 : 3;
+      }
+    }
+    __syncwarp();
+    const int a_kp = active ? Kp : 0, p_kp = pending ? pKp : 0;
+    const int a0 = __shfl_sync(0xffffffffu, a_kp, 0), a1 = __shfl_sync(0xffffffffu, a_kp, 16);
+    const int q0 = __shfl_sync(0xffffffffu, p_kp, 0), q1 = __shfl_sync(0xffffffffu, p_kp, 16);
+    const int wKp = a0 ? a0 : (a1 ? a1 : (q0 ? q0 : q1));
+    if (wKp == 0) break;   // nothing running, nothing waiting: the queue is empty
+    const int n = 4 * wKp, pitch = n + 2;
+    if (!active && pending && pKp == wKp) {
+      idx = pidx;
+      Kp = pKp;
+      pending = false;
+      active = true;
+      const double *st = io.state + idx * v2::STATE_STRIDE;
+      const double *ex = io.ext + idx * EXT_STRIDE;
+      for (int i = hl; i < NL; i += 16) sm[S_X + i] = st[i];
+      const unsigned long long bits = reinterpret_cast<const unsigned long long *>(st)[121];
+      const long long packed = reinterpret_cast<const long long *>(st)[122];
+      flags = 0;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int l = hl + 16 * t;
+        if (l < nn) {
+          sm[S_TEX + l] = st[41 + l];
+          sm[S_BETA + l] = st[81 + l];
+          sm[S_DNB + l] = ex[l];
+          sm[S_UPB + l] = ex[v2::MAXLINE + l];
+          flags |= (unsigned)((bits >> l) & 1ULL) << t;
+        }
+      }
+      nthick = (int)(packed & 0xffffffffLL);
+      topthick = (int)(packed >> 32);
+      const int nlead = n * (n + 2), nm = n * (LDB - n);
+      for (int e = hl; e < nlead; e += 16) sm[S_LEAD + e] = ex[EXT_LEAD + e];
+      for (int e = hl; e < nm; e += 16) sm[S_M + e] = ex[EXT_LEAD + nlead + e];
+      it = v2::IT_DECIDE;
+      cdmol = io.cdmol[idx];
+      cddv = cdmol / cfg.deltav_cms;
+      ++n_models;
+    }
+    __syncwarp();
+    // ---- one call of matrix(): radiative rates of the lead lines, lead block, M -------------------------------
+    double *B = sm + S_LEAD;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int l = hl + 16 * t;
+      if (l < nn) {
+        const int m = lmn[l] & 0xff, nlo = (lmn[l] >> 8) & 0xff;
+        if (max(m, nlo) < n) {
+          const double beta = sm[S_BETA + l], a = cs[C_LA + l];
+          const double exr = cs[C_LECOEF + l] * beta;
+          B[m * pitch + nlo] = sm[S_DNB + l] + a * (beta + exr);
+          B[nlo * pitch + m] = sm[S_UPB + l] + a * cs[C_LGR + l] * exr;
+        }
+      }
+    }
+    __syncwarp();
+    const double tot = lead_solve(sm, wKp, hl);
+    __syncwarp();
+    const double rtot = v2::rcp1(tot);
+    // ---- normalise, floor, under-relax + pyradex's stop test (v2::solve; lane l of 32 owned levels l and l + 32)
+    double dA = 0.0, dB = 0.0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int i = hl + ((t == 0) ? 0 : (t == 1) ? 32 : 16);
+      if (i < NL) {
+        const double xn = fmax(RB_MINPOP, sm[S_XNEW + i] * rtot);
+        const double prev = sm[S_X + i];
+        const double xo = (it == 0) ? xn : fmax(RB_MINPOP, prev);
+        const double xr = RB_F32(0.3) * xn + RB_F32(0.7) * xo;
+        sm[S_XNEW + i] = xn;
+        sm[S_X + i] = xr;
+        if (t == 2) dB += fabs(prev - xr); else dA += fabs(prev - xr);
+      }
+    }
+    const double diff = half_sum(dA + dB);
+    __syncwarp();
+    // ---- per line: Tex of this call, optical depth and escape probability of the next ------------------------
+    double tsA = 0.0, tsB = 0.0;
+    const int nthick_this = nthick;
+    nthick = 0;
+    topthick = -1;
+    unsigned nflags = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const int tt = (t == 0) ? 0 : (t == 1) ? 2 : 1;   // lines hl, hl + 32, hl + 16: the order of the 32-lane sums
+      const int l = hl + 16 * tt;
+      if (l < nn) {
+        const int mn = lmn[l];
+        const int m = mn & 0xff, nlo = (mn >> 8) & 0xff;
+        const double gr = cs[C_LGR + l];
+        const double xm = sm[S_XNEW + m], xn = sm[S_XNEW + nlo];
+        const bool floored = (xn <= RB_MINPOP) || (xm <= RB_MINPOP);
+        const double told = sm[S_TEX + l];
+        double thistex = told;
+        if (!floored) thistex = cs[C_LFKXNU + l] * v2::rcp1(v2::fast_log(xn * gr * v2::rcp1(xm)));
+        if (cfg.stop_rule == RB_STOP_RADEX && ((flags >> tt) & 1u)) {
+          if (tt == 1) tsB += fabs((thistex - told) / thistex); else tsA += fabs((thistex - told) / thistex);
+        }
+        sm[S_TEX + l] = (it == 0) ? thistex : 0.5 * (thistex + told);
+        const double tau = cddv * (sm[S_X + nlo] * gr - sm[S_X + m]) * cs[C_LTDEN + l];
+        if (tau > 1.0e-2) ++nthick;
+        if (tau > RB_F32(0.01)) nflags |= 1u << tt;
+        if (!(fabs(tau * 0.5) < RB_F32(0.01))) topthick = max(topthick, max(m, nlo));
+        sm[S_BETA + l] = v2::escprob_fast(tau, RB_GEOM_LVG);
+      }
+    }
+    flags = nflags;
+    topthick = half_max_int(topthick);
+    bool stop;
+    if (cfg.stop_rule == RB_STOP_RADEX) {
+      int conv = 0;
+      nthick = half_sum_int(nthick);
+      const double tsum = half_sum(tsA + tsB);
+      if (it >= 10) {
+        if (nthick_this == 0) conv = 1;
+        else if (tsum / nthick_this < RB_F32(1.0e-6)) conv = 1;
+      }
+      stop = conv != 0;
+    } else {
+      stop = (diff < cfg.abs_tol) && (it > cfg.miniter);
+    }
+    __syncwarp();
+    if (!active) continue;
+    ++n_cached;
+    // ---- what v2::solve decides at the bottom of this call and at the top of the next ---------------------------
+    bool hit_max = false, leave = false;
+    if (!stop) {
+      ++it;
+      if (it >= cfg.maxiter) hit_max = true;
+      else if (((topthick + 4) >> 2) > Kp) leave = true;
+    }
+    if (leave) {
+      // a frozen line turned thick: park for launch C, which re-captures with a larger lead block
+      double *st = io.state + idx * v2::STATE_STRIDE;
+      for (int i = hl; i < NL; i += 16) st[i] = sm[S_X + i];
+      unsigned long long bits = 0;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int l = hl + 16 * t;
+        if (l < nn) {
+          st[41 + l] = sm[S_TEX + l];
+          st[81 + l] = sm[S_BETA + l];
+        }
+        const unsigned b = (__ballot_sync(hmask, (flags >> t) & 1u) >> (16 * half)) & 0xffffu;
+        bits |= (unsigned long long)b << (16 * t);
+      }
+      if (hl == 0) {
+        reinterpret_cast<unsigned long long *>(st)[121] = bits;
+        reinterpret_cast<long long *>(st)[122] = ((long long)topthick << 32) | (long long)(unsigned)nthick;
+        reinterpret_cast<long long *>(st)[123] = v2::resume_word(it, 1);
+        io.order_c[atomicAdd(&io.sched_small[49], 1ULL)] = (int)idx;
+      }
+      iters += (unsigned long long)(it - v2::IT_DECIDE);
+      ++n_inval;
+      active = false;
+      __syncwarp(hmask);
+      continue;
+    }
+    if (!(stop || hit_max)) continue;
+    // ---- results (k_lvg_solve_v2's epilogue) --------------------------------------------------------------------
+    int nonfinite = 0;
+#pragma unroll 1
+    for (int l = hl; l < nn; l += 16) {
+      const int m = lmn[l] & 0xff, nlo = (lmn[l] >> 8) & 0xff;
+      const double xnu = mol.xnu[l];
+      const double xt = xnu * xnu * xnu;
+      const double hnu = RB_FK * xnu / cfg.tbg;
+      const double backi = (hnu >= 160.0) ? 1.0e-30 : RB_THC * xt / (exp(hnu) - 1.0);
+      const double tex = sm[S_TEX + l];
+      const double tau = (cdmol / cfg.deltav_cms) * (sm[S_XNEW + nlo] * cs[C_LGR + l] - sm[S_XNEW + m]) * cs[C_LTDEN + l];
+      const double ftau = exp(-tau);
+      const double earg = cfg.fk_epi * xnu / tex;
+      const double bnutex = cfg.thc_epi * xt / (exp(earg) - 1.0);
+      const double toti = backi * ftau + bnutex * (1.0 - ftau);
+      const double sf = toti - backi;
+      if (!isfinite(sf)) nonfinite = 1;
+      if (io.surf) io.surf[idx * nn + l] = sf;
+      if (io.tex) io.tex[idx * nn + l] = tex;
+      if (io.tau) io.tau[idx * nn + l] = tau;
+    }
+    if (io.xpop)
+      for (int i = hl; i < nl; i += 16) io.xpop[idx * nl + i] = sm[S_X + i];
+    nonfinite = __any_sync(hmask, nonfinite);
+    if (hl == 0) {
+      if (io.niter) io.niter[idx] = it;
+      if (io.status) io.status[idx] = (hit_max ? RB_ST_MAXITER : 0) | (nonfinite ? RB_ST_NONFINITE : 0);
+    }
+    iters += (unsigned long long)((hit_max ? it : it + 1) - v2::IT_DECIDE);
+    active = false;
+    __syncwarp(hmask);
+  }
+  (void)qnan;
+  if (hl == 0) {
+    if (iters) atomicAdd(&io.counters[1], iters);
+    if (cfg.stats && n_models) {
+      atomicAdd(&cfg.stats[0], n_cached);
+      atomicAdd(&cfg.stats[1], n_models);   // one capture each (made by launch B)
+      if (n_inval) atomicAdd(&cfg.stats[2], n_inval);
+    }
   }
 }
 
@@ -940,7 +1209,8 @@ SolveCfg make_cfg(const rb_ctx *ctx, const rb_opts *o, double deltav_kms, double
   c.fk_epi = d.fk_epi;
   c.thc_epi = d.thc_epi;
   c.cache = (d.kernel != 2);
-  c.sched = (d.kernel == 0);
+  c.sched = (d.kernel == 0 || d.kernel == 4);
+  c.small = (d.kernel == 4);
   c.stats = ctx->counters + 3;
   return c;
 }
@@ -983,7 +1253,7 @@ Launch v1_launch(rb_ctx *ctx, long long n) {
 
 bool use_v2(const rb_ctx *ctx, const rb_opts *o) {
   const int kernel = o ? o->kernel : 0;
-  return kernel != 1 && kernel <= 3 && kernel >= 0 && ctx->mol.nlev == v2::NL && ctx->mol.nline <= v2::MAXLINE;
+  return kernel != 1 && kernel <= 4 && kernel >= 0 && ctx->mol.nlev == v2::NL && ctx->mol.nline <= v2::MAXLINE;
 }
 
 Launch v2_launch(rb_ctx *ctx, long long n) {
@@ -1113,6 +1383,9 @@ int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
     if (mol->nlev == v2::NL && mol->nline <= v2::MAXLINE) {
       const int sm2 = (int)(V2_WARPS * v2::SLAB * sizeof(double));
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_solve_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_lvg_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((v2s::CSLAB + 2 * VS_WARPS * v2s::SSLAB) * sizeof(double)));
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess)
@@ -1179,19 +1452,30 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
   if (use_v2(ctx, opts)) {
     const Launch L = v2_launch(ctx, n);
     if (cfg.sched && cfg.cache && geometry == RB_GEOM_LVG && n >= RB_SCHED_MIN) {
-      // two launches with the parked models ordered by the lead-block size they will run with (lvg_v2.cuh)
+      // two launches with the parked models ordered by the lead-block size they will run with (lvg_v2.cuh);
+      // with the half-warp engine (lvg_small.cuh) launch B only captures the models with small lead blocks,
+      // k_lvg_small iterates them and launch C finishes the few whose frozen lines turn thick
+      const bool small = cfg.small != 0;
       const size_t b_state = align256((size_t)n * v2::STATE_STRIDE * sizeof(double)), b_int = align256((size_t)n * sizeof(int));
-      if (b_state + 2 * b_int > ctx->sched_bytes) {
+      const size_t b_ext = small ? align256((size_t)n * v2::EXT_STRIDE * sizeof(double)) : 0;
+      const size_t b_all = b_state + (small ? 3 : 2) * b_int + b_ext;
+      if (b_all > ctx->sched_bytes) {
         if (ctx->sched_buf) cudaFree(ctx->sched_buf);
         ctx->sched_buf = nullptr;
         ctx->sched_bytes = 0;
-        CUDA_TRY(cudaMalloc(&ctx->sched_buf, b_state + 2 * b_int));
-        ctx->sched_bytes = b_state + 2 * b_int;
+        CUDA_TRY(cudaMalloc(&ctx->sched_buf, b_all));
+        ctx->sched_bytes = b_all;
       }
       if (!ctx->sched_small) CUDA_TRY(cudaMalloc(&ctx->sched_small, 64 * sizeof(unsigned long long)));
-      io.state = static_cast<double *>(ctx->sched_buf);
-      io.keys = reinterpret_cast<int *>(static_cast<char *>(ctx->sched_buf) + b_state);
-      int *order = reinterpret_cast<int *>(static_cast<char *>(ctx->sched_buf) + b_state + b_int);
+      char *base = static_cast<char *>(ctx->sched_buf);
+      io.state = reinterpret_cast<double *>(base);
+      io.keys = reinterpret_cast<int *>(base + b_state);
+      int *order = reinterpret_cast<int *>(base + b_state + b_int);
+      io.sched_small = ctx->sched_small;
+      if (small) {
+        io.order_c = reinterpret_cast<int *>(base + b_state + 2 * b_int);
+        io.ext = reinterpret_cast<double *>(base + b_state + 3 * b_int);
+      }
       CUDA_TRY(cudaMemsetAsync(ctx->sched_small, 0, 64 * sizeof(unsigned long long), ctx->stream));
       io.sched = 1;
       k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
@@ -1204,6 +1488,18 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
       io.order = order;
       io.n_parked = ctx->sched_small + 48;
       k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+      if (small) {
+        const size_t sm_s = (size_t)(v2s::CSLAB + 2 * VS_WARPS * v2s::SSLAB) * sizeof(double);
+        CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+        k_lvg_small<<<ctx->sm_count, VS_WARPS * 32, sm_s, ctx->stream>>>(ctx->mol, cfg, io);
+        CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+        io.sched = 4;
+        io.order = io.order_c;
+        io.n_parked = ctx->sched_small + 49;
+        io.ext = nullptr;
+        k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+        ctx->launches += 2;
+      }
       ctx->launches += 4;
     } else {
       k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);

@@ -243,6 +243,26 @@ def test_two_launch_schedule_is_bit_identical(ctx):
             np.testing.assert_array_equal(a[k], b[k], err_msg="%s %s" % (k, kw))
 
 
+def test_half_warp_engine_is_bit_identical(ctx):
+    """kernel=4: models with lead blocks of <= 16 levels run their cached iterations two per warp in
+    k_lvg_small (capture parked by launch B, invalidated models finished by launch C).  Same arithmetic
+    per model as the single launch (kernel=3): every output and the iteration total match bit for bit."""
+    P = draw_params(np.random.default_rng(34), 20000, 10.926)
+    P[9, 0] = 2.0e4         # T out of range
+    P[770, 2] = 1.0         # N out of range
+    for kw in ({}, {"maxiter": 2}, {"maxiter": 5}, {"maxiter": 40}, {"stop_rule": _lib.STOP_RADEX}):
+        a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, kernel=4, **kw)
+        ita, _ = ctx.counters()
+        sa = ctx.cache_stats()
+        b = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, kernel=3, **kw)
+        itb, _ = ctx.counters()
+        sb = ctx.cache_stats()
+        assert ita == itb, (kw, ita, itb)
+        assert tuple(sa) == tuple(sb), (kw, sa, sb)
+        for k in ("xpop", "tex", "tau", "surf", "niter", "status"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg="%s %s" % (k, kw))
+
+
 def test_determinism(ctx):
     P = draw_params(np.random.default_rng(9), 200, 10.926)
     a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926)
