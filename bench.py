@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--sort", default="", help="debug: order the models by cd | tk | top (highest thick line, from a first pass)")
     ap.add_argument("--keep", default="", help="debug: small | big -- keep only the models whose lead block (from a first pass) has <= 16 | > 16 levels, tiled to n")
     ap.add_argument("--same", type=int, default=-1, help="debug: every model is a copy of draw #SAME (I-cache experiments)")
-    ap.add_argument("--kernel", type=int, default=0, help="rb_opts.kernel: 0 default, 1 v1 LU, 2 v2 without caching")
+    ap.add_argument("--kernel", type=int, default=0, help="rb_opts.kernel: 0 default, 1 v1 LU, 2 v2 without caching, 3 single launch, 4 without the half-warp engine")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -309,10 +309,10 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "models_per_gpu": n, "l2": "256 MiB flush write between timed steps",
                        "outputs": "xpop,tex,tau,surf,niter,status",
-                       "kernel": {0: "k_lvg_solve_v2 (frozen-top caching, two launches ordered by lead-block size)",
+                       "kernel": {0: "k_lvg_solve_v2 launches A, B, C (frozen-top caching, ordered by lead-block size) + k_lvg_small (half-warp engine for lead blocks <= 16 levels)",
                                   1: "k_lvg_solve_v1", 2: "k_lvg_solve_v2 (no caching)",
                                   3: "k_lvg_solve_v2 (frozen-top caching, single launch)",
-                                  4: "k_lvg_solve_v2 launches A, B, C + k_lvg_small (half-warp engine for lead blocks <= 16 levels)"}[args.kernel]},
+                                  4: "k_lvg_solve_v2 (frozen-top caching, two launches ordered by lead-block size)"}[args.kernel]},
             "iters_per_solve": iters_all / (world * n),
             "matrix_iterations_per_s": iters_all / (ms_per_step * 1e-3),
             "frac_iterations_cached": cache_stats[0] / max(1, total_iters),

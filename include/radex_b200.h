@@ -50,9 +50,12 @@ typedef struct rb_opts {
   int32_t stop_rule;   /* rb_stop_rule                                                    */
   int32_t miniter;     /* 10  (core.py:460-461)                                           */
   int32_t maxiter;     /* 200 (core.py:462-463)                                           */
-  int32_t kernel;      /* 0 = default (fastest validated), 1 = v1 shared-memory pivoted LU,
+  int32_t kernel;      /* 0 = default (fastest validated: v2, launches ordered by lead-block size,
+                              half-warp engine for small lead blocks),
+                          1 = v1 shared-memory pivoted LU,
                           2 = v2 without frozen-top caching (cross-check / A-B),
-                          3 = v2 with caching but as a single launch (no two-launch ordering)  */
+                          3 = v2 with caching but as a single launch (no ordering),
+                          4 = v2 with ordered launches but without the half-warp engine (A-B)  */
   double abs_tol;      /* 1e-16 (core.py:857)                                             */
   double fk_epi;       /* h c / k_B used by the brightness epilogue (astropy, core.py:981-984) */
   double thc_epi;      /* 2 h c     used by the brightness epilogue                        */

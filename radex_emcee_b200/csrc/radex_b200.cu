@@ -61,8 +61,8 @@ struct SolveCfg {
   int method, stop_rule, miniter, maxiter;
   double abs_tol, fk_epi, thc_epi;
   int cache;                    // v2: frozen-top caching enabled (rb_opts.kernel != 2)
-  int sched;                    // v2: two-launch scheduling allowed (rb_opts.kernel == 0 or 4)
-  int small;                    // v2: half-warp engine for lead blocks <= 16 levels (lvg_small.cuh)
+  int sched;                    // v2: launch scheduling allowed (rb_opts.kernel == 0 or 4)
+  int small;                    // v2: half-warp engine for lead blocks <= 16 levels (lvg_small.cuh; kernel == 0)
   unsigned long long *stats;    // v2: [0] cached iterations, [1] captures, [2] invalidations
 };
 
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
     const double cdmol = io.cdmol[idx];
     const int it = v2::solve(mol, sm, gB, phase, lane, io.tkin[idx], dens, cdmol, cfg, &st, io.sched,
                              io.state ? io.state + idx * v2::STATE_STRIDE : nullptr, &key,
-                             (io.sched == 2 && io.ext) ? io.ext + idx * v2::EXT_STRIDE : nullptr);
+                             (io.sched == 1 && io.ext) ? io.ext + idx * v2::EXT_STRIDE : nullptr);
     if (io.sched == 1 && lane == 0) io.keys[idx] = (st & v2::ST_PARKED) ? key : -1;
     if (st & v2::ST_PARKED) {   // launch B finishes this model
       iters += (unsigned long long)it;
@@ -1210,7 +1210,7 @@ SolveCfg make_cfg(const rb_ctx *ctx, const rb_opts *o, double deltav_kms, double
   c.thc_epi = d.thc_epi;
   c.cache = (d.kernel != 2);
   c.sched = (d.kernel == 0 || d.kernel == 4);
-  c.small = (d.kernel == 4);
+  c.small = (d.kernel == 0);
   c.stats = ctx->counters + 3;
   return c;
 }
@@ -1455,7 +1455,7 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
       // two launches with the parked models ordered by the lead-block size they will run with (lvg_v2.cuh);
       // with the half-warp engine (lvg_small.cuh) launch B only captures the models with small lead blocks,
       // k_lvg_small iterates them and launch C finishes the few whose frozen lines turn thick
-      const bool small = cfg.small != 0;
+      const bool small = cfg.small != 0 && n <= (1LL << 21);   // the parked captures take 6.3 KB per model
       const size_t b_state = align256((size_t)n * v2::STATE_STRIDE * sizeof(double)), b_int = align256((size_t)n * sizeof(int));
       const size_t b_ext = small ? align256((size_t)n * v2::EXT_STRIDE * sizeof(double)) : 0;
       const size_t b_all = b_state + (small ? 3 : 2) * b_int + b_ext;
@@ -1486,7 +1486,8 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
       CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));   // queue head only
       io.sched = 2;
       io.order = order;
-      io.n_parked = ctx->sched_small + 48;
+      // heaviest key first: with the half-warp engine launch B stops where key 4 begins
+      io.n_parked = ctx->sched_small + (small ? 16 + v2::KP_SMALL_MAX : 48);
       k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
       if (small) {
         const size_t sm_s = (size_t)(v2s::CSLAB + 2 * VS_WARPS * v2s::SSLAB) * sizeof(double);
