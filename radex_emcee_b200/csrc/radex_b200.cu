@@ -82,6 +82,8 @@ struct rb_ctx {
   void *sched_buf = nullptr;              // v2 scheduling: parked state, keys, order (grow-only)
   size_t sched_bytes = 0;
   unsigned long long *sched_small = nullptr;   // 64 words: histogram, offsets, cursors, parked count
+  void *ln_buf = nullptr;                 // lnprob pipeline: model parameters, observed-line brightness, status (grow-only)
+  size_t ln_bytes = 0;
   long long launches = 0;
   long long last_total_iters = 0;
 };
@@ -481,6 +483,10 @@ struct SolveIO {
   const unsigned long long *n_parked;  // launch B: number of parked models (device)
   // half-warp engine (lvg_small.cuh): launch B parks the captures of small-lead models in ext, k_lvg_small runs
   // them and appends the ones whose frozen lines turn thick to order_c for launch C (sched = 4)
+  // observed-line mode (lnprob pipeline): only the brightness of nobs lines is written, obs_surf[n][RB_MAX_OBS]
+  double *obs_surf;
+  int nobs;
+  int obs_line[RB_MAX_OBS];
   double *ext;                         // n x v2s::EXT_STRIDE
   unsigned long long *sched_small;     // [16+k] first queue position of key k, [48] parked, [49] models for launch C
   int *order_c;
@@ -657,6 +663,8 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
 // ------------------------------------------------------------------------------------------------
 #define V2_WARPS 12
 #define RB_SCHED_MIN 8192   // batches smaller than this run as one launch
+#define RB_LNPROB_PIPE_MIN 16384   // walkers per call from which lnprob runs as a pipeline (measured: 2 components,
+                                   // 8192 walkers per call: fused launch 7 % faster; 1 component, 16384: pipeline 41 % faster)
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, SolveCfg cfg, SolveIO io) {
   extern __shared__ double smem[];
@@ -692,8 +700,13 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
     const bool bad = (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) != 0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     int nonfinite = 0;
+    if (io.obs_surf && lane < io.nobs) {
+      double tex, tau, sf = qnan;
+      if (!bad) v2::line_results(mol, sm, io.obs_line[lane], cdmol, cfg, tex, tau, sf);
+      io.obs_surf[idx * RB_MAX_OBS + lane] = sf;
+    }
 #pragma unroll 1
-    for (int l = lane; l < nn; l += 32) {
+    for (int l = io.obs_surf ? nn : lane; l < nn; l += 32) {
       double tex = qnan, tau = qnan, sf = qnan;
       if (!bad) {
         v2::line_results(mol, sm, l, cdmol, cfg, tex, tau, sf);
@@ -968,8 +981,10 @@ __global__ void __launch_bounds__(VS_WARPS * 32, 1) k_lvg_small(MolDev mol, Solv
     if (!(stop || hit_max)) continue;
     // ---- results (k_lvg_solve_v2's epilogue) --------------------------------------------------------------------
     int nonfinite = 0;
+    const int l_first = io.obs_surf ? ((hl < io.nobs) ? io.obs_line[hl] : nn) : hl;
+    const int l_step = io.obs_surf ? nn : 16;
 #pragma unroll 1
-    for (int l = hl; l < nn; l += 16) {
+    for (int l = l_first; l < nn; l += l_step) {
       const int m = lmn[l] & 0xff, nlo = (lmn[l] >> 8) & 0xff;
       const double xnu = mol.xnu[l];
       const double xt = xnu * xnu * xnu;
@@ -982,6 +997,10 @@ __global__ void __launch_bounds__(VS_WARPS * 32, 1) k_lvg_small(MolDev mol, Solv
       const double bnutex = cfg.thc_epi * xt / (exp(earg) - 1.0);
       const double toti = backi * ftau + bnutex * (1.0 - ftau);
       const double sf = toti - backi;
+      if (io.obs_surf) {
+        io.obs_surf[idx * RB_MAX_OBS + hl] = sf;
+        continue;
+      }
       if (!isfinite(sf)) nonfinite = 1;
       if (io.surf) io.surf[idx * nn + l] = sf;
       if (io.tex) io.tex[idx * nn + l] = tex;
@@ -1088,6 +1107,92 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lnprob_v2(MolDev mol, Solv
   }
   if (lane == 0) {
     if (iters) atomicAdd(&io.counters[1], iters);
+    if (solves) atomicAdd(&io.counters[2], solves);
+  }
+}
+
+// ---- lnprob as a pipeline for large ensembles: priors and walker -> model parameters (k_lnprob_expand), the
+// scheduled solve of all n x NCOMP models with the half-warp engine (launch_solve_pipeline), fluxes -> chi^2
+// (k_lnprob_combine).  Same expressions as the fused k_lnprob_v2, which stays the path of small ensembles.
+struct LnprobPipe {
+  double *tkin, *dens, *cdmol;   // n x NCOMP models
+  double *obs_surf;              // [n x NCOMP][RB_MAX_OBS]
+  int *status;
+};
+
+template <int NCOMP>
+__global__ void k_lnprob_expand(MolDev mol, LnprobIO io, LnprobPipe pp) {
+  constexpr int ND = 4 * NCOMP;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= io.n) return;
+  double p[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) p[i] = io.P[idx * ND + i];
+  const double lp = (NCOMP == 1) ? lnprior1(p, io.bounds) : lnprior2(p, io.bounds, io.has_td, io.t_d);
+  io.lnp[idx] = lp;   // the prior waits here for k_lnprob_combine
+  const double fortho = 3.0 / (1.0 + 3.0);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+  for (int c = 0; c < NCOMP; ++c) {
+    const long long m = idx * NCOMP + c;
+    const bool go = isfinite(lp);   // prior short-circuit: a NaN temperature is refused before any work is done
+    const double dens_tot = pow(10.0, p[4 * c + 0]);
+    for (int q = 0; q < mol.npart; ++q)
+      pp.dens[m * mol.npart + q] = (mol.part_id[q] == 2) ? (1.0 - fortho) * dens_tot
+                                   : (mol.part_id[q] == 3) ? fortho * dens_tot : 0.0;
+    pp.tkin[m] = go ? pow(10.0, p[4 * c + 1]) : qnan;
+    pp.cdmol[m] = pow(10.0, p[4 * c + 2]);
+  }
+}
+
+template <int NCOMP>
+__global__ void k_lnprob_combine(LnprobIO io, LnprobPipe pp) {
+  constexpr int ND = 4 * NCOMP;
+  const int lane = threadIdx.x & 31;
+  const long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;   // one warp per walker
+  if (idx >= io.n) return;
+  const double lp = io.lnp[idx];
+  double result = neg_inf();
+  unsigned long long solves = 0;
+  if (isfinite(lp)) {
+    double model = 0.0;
+    bool value_error = false;
+#pragma unroll
+    for (int c = 0; c < NCOMP; ++c) {
+      const long long m = idx * NCOMP + c;
+      if (pp.status[m] & (RB_ST_T_RANGE | RB_ST_N_RANGE)) {
+        value_error = true;
+      } else {
+        ++solves;
+        if (lane < io.obs.nobs) model += pp.obs_surf[m * RB_MAX_OBS + lane] * pow(10.0, io.P[idx * ND + 4 * c + 3]) * 1.0e23;
+      }
+    }
+    if (!value_error) {
+      int bad = 0;
+      double r2 = 0.0, le = 0.0;
+      if (lane < io.obs.nobs) {
+        const double f = io.obs.flux[lane];
+        const double e = fmax(fabs(io.obs.eflux[lane]), 1.0e-12);
+        if (!isfinite(f) || !isfinite(model) || !isfinite(e)) {
+          bad = 1;
+        } else {
+          const double r = (f - model) / e;
+          const double max_safe = 1.3407807929942596e+153;  // sqrt(DBL_MAX)/10
+          if (!isfinite(r) || fabs(r) > max_safe) bad = 1;
+          r2 = r * r;
+          le = log(e);
+        }
+      }
+      bad = __any_sync(0xffffffffu, bad);
+      const double chi2 = warp_sum(r2), logterm = 2.0 * warp_sum(le);
+      if (!bad) {
+        const double ll = -0.5 * (chi2 + logterm);
+        result = isfinite(ll) ? lp + ll : neg_inf();
+      }
+    }
+  }
+  if (lane == 0) {
+    io.lnp[idx] = result;
     if (solves) atomicAdd(&io.counters[2], solves);
   }
 }
@@ -1413,6 +1518,7 @@ void rb_ctx_destroy(rb_ctx *ctx) {
   if (ctx->bslab) cudaFree(ctx->bslab);
   if (ctx->sched_buf) cudaFree(ctx->sched_buf);
   if (ctx->sched_small) cudaFree(ctx->sched_small);
+  if (ctx->ln_buf) cudaFree(ctx->ln_buf);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1435,6 +1541,61 @@ int rb_ctx_reset_stream(rb_ctx *ctx) {
   return RB_OK;
 }
 
+// The scheduled solve of a large batch (lvg_v2.cuh, lvg_small.cuh): launch A, counting sort by lead-block size,
+// launch B (large lead blocks), k_lvg_small (small ones, two per warp), launch C (invalidated small ones).
+static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg, SolveIO io, const Launch &L) {
+  const long long n = io.n;
+  const bool small = cfg.small != 0 && n <= (1LL << 21);   // the parked captures take 6.3 KB per model
+  const size_t b_state = align256((size_t)n * v2::STATE_STRIDE * sizeof(double)), b_int = align256((size_t)n * sizeof(int));
+  const size_t b_ext = small ? align256((size_t)n * v2::EXT_STRIDE * sizeof(double)) : 0;
+  const size_t b_all = b_state + (small ? 3 : 2) * b_int + b_ext;
+  if (b_all > ctx->sched_bytes) {
+    if (ctx->sched_buf) cudaFree(ctx->sched_buf);
+    ctx->sched_buf = nullptr;
+    ctx->sched_bytes = 0;
+    CUDA_TRY(cudaMalloc(&ctx->sched_buf, b_all));
+    ctx->sched_bytes = b_all;
+  }
+  if (!ctx->sched_small) CUDA_TRY(cudaMalloc(&ctx->sched_small, 64 * sizeof(unsigned long long)));
+  char *base = static_cast<char *>(ctx->sched_buf);
+  io.state = reinterpret_cast<double *>(base);
+  io.keys = reinterpret_cast<int *>(base + b_state);
+  int *order = reinterpret_cast<int *>(base + b_state + b_int);
+  io.sched_small = ctx->sched_small;
+  if (small) {
+    io.order_c = reinterpret_cast<int *>(base + b_state + 2 * b_int);
+    io.ext = reinterpret_cast<double *>(base + b_state + 3 * b_int);
+  }
+  CUDA_TRY(cudaMemsetAsync(ctx->sched_small, 0, 64 * sizeof(unsigned long long), ctx->stream));
+  io.sched = 1;
+  k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  const int tpb = 256, nb = (int)((n + tpb - 1) / tpb);
+  k_sched_hist<<<nb, tpb, 0, ctx->stream>>>(io.keys, n, ctx->sched_small);
+  k_sched_scan<<<1, 1, 0, ctx->stream>>>(ctx->sched_small);
+  k_sched_scatter<<<nb, tpb, 0, ctx->stream>>>(io.keys, n, ctx->sched_small, order);
+  CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));   // queue head only
+  io.sched = 2;
+  io.order = order;
+  // heaviest key first: with the half-warp engine launch B stops where key 4 begins
+  io.n_parked = ctx->sched_small + (small ? 16 + v2::KP_SMALL_MAX : 48);
+  k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  if (small) {
+    const size_t sm_s = (size_t)(v2s::CSLAB + 2 * VS_WARPS * v2s::SSLAB) * sizeof(double);
+    CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+    k_lvg_small<<<ctx->sm_count, VS_WARPS * 32, sm_s, ctx->stream>>>(ctx->mol, cfg, io);
+    CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+    io.sched = 4;
+    io.order = io.order_c;
+    io.n_parked = ctx->sched_small + 49;
+    io.ext = nullptr;
+    k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+    ctx->launches += 2;
+  }
+  ctx->launches += 4;
+  CUDA_TRY(cudaGetLastError());
+  return RB_OK;
+}
+
 int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double *dens, const double *cdmol,
                        double deltav_kms, double tbg, int geometry, const rb_opts *opts, double *xpop,
                        double *tex, double *tau, double *surf, int32_t *niter, int32_t *status) {
@@ -1452,56 +1613,8 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
   if (use_v2(ctx, opts)) {
     const Launch L = v2_launch(ctx, n);
     if (cfg.sched && cfg.cache && geometry == RB_GEOM_LVG && n >= RB_SCHED_MIN) {
-      // two launches with the parked models ordered by the lead-block size they will run with (lvg_v2.cuh);
-      // with the half-warp engine (lvg_small.cuh) launch B only captures the models with small lead blocks,
-      // k_lvg_small iterates them and launch C finishes the few whose frozen lines turn thick
-      const bool small = cfg.small != 0 && n <= (1LL << 21);   // the parked captures take 6.3 KB per model
-      const size_t b_state = align256((size_t)n * v2::STATE_STRIDE * sizeof(double)), b_int = align256((size_t)n * sizeof(int));
-      const size_t b_ext = small ? align256((size_t)n * v2::EXT_STRIDE * sizeof(double)) : 0;
-      const size_t b_all = b_state + (small ? 3 : 2) * b_int + b_ext;
-      if (b_all > ctx->sched_bytes) {
-        if (ctx->sched_buf) cudaFree(ctx->sched_buf);
-        ctx->sched_buf = nullptr;
-        ctx->sched_bytes = 0;
-        CUDA_TRY(cudaMalloc(&ctx->sched_buf, b_all));
-        ctx->sched_bytes = b_all;
-      }
-      if (!ctx->sched_small) CUDA_TRY(cudaMalloc(&ctx->sched_small, 64 * sizeof(unsigned long long)));
-      char *base = static_cast<char *>(ctx->sched_buf);
-      io.state = reinterpret_cast<double *>(base);
-      io.keys = reinterpret_cast<int *>(base + b_state);
-      int *order = reinterpret_cast<int *>(base + b_state + b_int);
-      io.sched_small = ctx->sched_small;
-      if (small) {
-        io.order_c = reinterpret_cast<int *>(base + b_state + 2 * b_int);
-        io.ext = reinterpret_cast<double *>(base + b_state + 3 * b_int);
-      }
-      CUDA_TRY(cudaMemsetAsync(ctx->sched_small, 0, 64 * sizeof(unsigned long long), ctx->stream));
-      io.sched = 1;
-      k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
-      const int tpb = 256, nb = (int)((n + tpb - 1) / tpb);
-      k_sched_hist<<<nb, tpb, 0, ctx->stream>>>(io.keys, n, ctx->sched_small);
-      k_sched_scan<<<1, 1, 0, ctx->stream>>>(ctx->sched_small);
-      k_sched_scatter<<<nb, tpb, 0, ctx->stream>>>(io.keys, n, ctx->sched_small, order);
-      CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));   // queue head only
-      io.sched = 2;
-      io.order = order;
-      // heaviest key first: with the half-warp engine launch B stops where key 4 begins
-      io.n_parked = ctx->sched_small + (small ? 16 + v2::KP_SMALL_MAX : 48);
-      k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
-      if (small) {
-        const size_t sm_s = (size_t)(v2s::CSLAB + 2 * VS_WARPS * v2s::SSLAB) * sizeof(double);
-        CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
-        k_lvg_small<<<ctx->sm_count, VS_WARPS * 32, sm_s, ctx->stream>>>(ctx->mol, cfg, io);
-        CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
-        io.sched = 4;
-        io.order = io.order_c;
-        io.n_parked = ctx->sched_small + 49;
-        io.ext = nullptr;
-        k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
-        ctx->launches += 2;
-      }
-      ctx->launches += 4;
+      rc = launch_solve_pipeline(ctx, cfg, io, L);
+      if (rc != RB_OK) return rc;
     } else {
       k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
     }
@@ -1594,7 +1707,46 @@ static int lnprob_dev(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const 
   io.has_td = has_td;
   io.t_d = t_d;
   io.counters = ctx->counters;
-  if (use_v2(ctx, opts)) {
+  if (use_v2(ctx, opts) && cfg.sched && cfg.small && cfg.cache && n >= RB_LNPROB_PIPE_MIN) {
+    // large ensembles: expand -> scheduled solve of all n x ncomp models (half-warp engine) -> combine
+    const long long m = n * ncomp;
+    const int np = ctx->mol.npart;
+    const size_t b_d = align256((size_t)m * sizeof(double)), b_dn = align256((size_t)m * np * sizeof(double));
+    const size_t b_o = align256((size_t)m * RB_MAX_OBS * sizeof(double)), b_s = align256((size_t)m * sizeof(int));
+    const size_t b_all = 2 * b_d + b_dn + b_o + b_s;
+    if (b_all > ctx->ln_bytes) {
+      if (ctx->ln_buf) cudaFree(ctx->ln_buf);
+      ctx->ln_buf = nullptr;
+      ctx->ln_bytes = 0;
+      CUDA_TRY(cudaMalloc(&ctx->ln_buf, b_all));
+      ctx->ln_bytes = b_all;
+    }
+    char *base = static_cast<char *>(ctx->ln_buf);
+    LnprobPipe pp;
+    pp.tkin = reinterpret_cast<double *>(base);
+    pp.cdmol = reinterpret_cast<double *>(base + b_d);
+    pp.dens = reinterpret_cast<double *>(base + 2 * b_d);
+    pp.obs_surf = reinterpret_cast<double *>(base + 2 * b_d + b_dn);
+    pp.status = reinterpret_cast<int *>(base + 2 * b_d + b_dn + b_o);
+    const int tpb = 256;
+    SolveIO sio{m, pp.tkin, pp.dens, pp.cdmol, nullptr, nullptr, nullptr, nullptr, nullptr, pp.status, ctx->counters,
+                0, nullptr, nullptr, nullptr, nullptr};
+    sio.obs_surf = pp.obs_surf;
+    sio.nobs = obs->nobs;
+    for (int i = 0; i < obs->nobs; ++i) sio.obs_line[i] = obs->jup[i] - 1;
+    if (ncomp == 1)
+      k_lnprob_expand<1><<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(ctx->mol, io, pp);
+    else
+      k_lnprob_expand<2><<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(ctx->mol, io, pp);
+    int rc = launch_solve_pipeline(ctx, cfg, sio, v2_launch(ctx, m));
+    if (rc != RB_OK) return rc;
+    const unsigned nbc = (unsigned)((n * 32 + tpb - 1) / tpb);
+    if (ncomp == 1)
+      k_lnprob_combine<1><<<nbc, tpb, 0, ctx->stream>>>(io, pp);
+    else
+      k_lnprob_combine<2><<<nbc, tpb, 0, ctx->stream>>>(io, pp);
+    ctx->launches += 2;
+  } else if (use_v2(ctx, opts)) {
     const Launch L = v2_launch(ctx, n);
     if (ncomp == 1)
       k_lnprob_v2<1><<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);

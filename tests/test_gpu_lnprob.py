@@ -101,3 +101,38 @@ def test_lnlike_edge_semantics(oracle):
     e0 = np.zeros_like(eflux)                           # floored at 1e-12 -> huge but finite chi^2
     a, b = er1.lnprob(p0, jup, flux, e0, bounds=bounds), oracle.lnprob1(p0, jup, flux, e0, bounds, tbg)
     assert np.isfinite(a) and abs(a / b - 1) < 1e-6
+
+
+def test_lnprob_pipeline_equals_fused_kernel():
+    """Large ensembles (>= 16384 walkers per call) run lnprob as a pipeline -- priors and parameters, the scheduled
+    solve with the half-warp engine, fluxes -> chi^2; small ones as one fused launch (kernel=3 forces it).  Same
+    arithmetic per model: identical -inf pattern, solve counts and values."""
+    from radex_emcee_b200 import _lib
+    rng = np.random.default_rng(11)
+    # two components
+    data = read_data(ROOT + "/data/flux_for2p.dat")
+    z, T_d, lw, jup, flux, eflux = get_source("G09v1.97", data)
+    tbg, ra, bounds, p0 = er2.source_setup(z)
+    er2.R = None
+    er2.init_radex(tbg)
+    er2.R.set_params(tbg=tbg)
+    P = p0 + rng.standard_normal((15000, 8)) * np.array([0.4, 0.1, 0.4, 0.3, 0.4, 0.2, 0.4, 0.3])
+    P = np.vstack([P, rng.uniform(bounds[:, 0] - 0.02, bounds[:, 1] + 0.02, size=(3000, 8))])
+    a, na = er2.lnprob(P, jup, flux, eflux, bounds=bounds, T_d=T_d, return_nsolves=True)
+    b, nb = er2.lnprob(P, jup, flux, eflux, bounds=bounds, T_d=T_d, opts=_lib.default_opts(kernel=3), return_nsolves=True)
+    assert na == nb and np.isfinite(a).sum() > 1000
+    np.testing.assert_array_equal(np.isfinite(a), np.isfinite(b))
+    fin = np.isfinite(a)
+    np.testing.assert_allclose(a[fin], b[fin], rtol=1e-13, atol=0)
+    # one component
+    z, jup, flux, eflux, tbg, bounds, p0 = _source1()
+    er1.R = None
+    er1.init_radex(tbg)
+    er1.R.set_params(tbg=tbg)
+    P = np.vstack([_walkers1(rng, bounds, 6000), p0 + 1e-2 * rng.standard_normal((12000, 4))])
+    a, na = er1.lnprob(P, jup, flux, eflux, bounds=bounds, return_nsolves=True)
+    b, nb = er1.lnprob(P, jup, flux, eflux, bounds=bounds, opts=_lib.default_opts(kernel=3), return_nsolves=True)
+    assert na == nb and np.isfinite(a).sum() > 1000
+    np.testing.assert_array_equal(np.isfinite(a), np.isfinite(b))
+    fin = np.isfinite(a)
+    np.testing.assert_allclose(a[fin], b[fin], rtol=1e-13, atol=0)

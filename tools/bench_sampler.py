@@ -24,6 +24,8 @@ ap.add_argument("--walkers", type=int, default=0)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--stop", default="pyradex")
+ap.add_argument("--kernel", type=int, default=0, help="rb_opts.kernel (3 forces the fused single-launch lnprob)")
+ap.add_argument("--spread", type=float, default=1e-3, help="sigma of the starting ball around p0")
 args = ap.parse_args()
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
@@ -39,9 +41,9 @@ else:
     tbg, ra, bounds, p0 = er2.source_setup(z)
     p0[3] += 0.1      # cold size > warm size so the whole starting ball has a finite prior
 ctx = _lib.Context(_lib.MolData(os.path.join(ROOT, "radex_emcee_b200", "data", "co.dat")), lr)
-opts = _lib.default_opts(stop_rule=0 if args.stop == "pyradex" else 1)
+opts = _lib.default_opts(stop_rule=0 if args.stop == "pyradex" else 1, kernel=args.kernel)
 eng = CudaEngine(ctx, SLEDModel(args.ncomp, jup, flux, eflux, bounds, tbg, T_d=T_d, opts=opts))
-pos = p0 + 1e-3 * np.random.default_rng(20170914).standard_normal((nw, 4 * args.ncomp))
+pos = p0 + args.spread * np.random.default_rng(20170914).standard_normal((nw, 4 * args.ncomp))
 s = StretchSampler(nw, 4 * args.ncomp, eng, seed=1)
 s.run_mcmc(pos, args.warmup, store=False)
 torch.cuda.synchronize()
@@ -69,6 +71,6 @@ if rank == 0:
     print(json.dumps({"metric": "walker-steps/s", "value": nw * args.steps / (t_ms * 1e-3), "n_gpus": world, "walkers": nw,
                       "ncomp": args.ncomp, "steps": args.steps, "ms_per_step": t_ms / args.steps, "solves_per_s": solves / (t_ms * 1e-3),
                       "solves_per_walker_step": solves / (nw * args.steps), "acceptance_fraction": acc, "wall_s": wall,
-                      "stop": args.stop, "launches": eng.launches}))
+                      "stop": args.stop, "kernel": args.kernel, "launches": eng.launches}))
 if world > 1:
     dist.destroy_process_group()
