@@ -124,7 +124,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sort", default="", help="debug: order the models by cd | tk | top (highest thick line, from a first pass)")
-    ap.add_argument("--keep", default="", help="debug: small | big -- keep only the models whose lead block (from a first pass) has <= 16 | > 16 levels, tiled to n")
+    ap.add_argument("--keep", default="", help="debug: small | big | k57 | k8 -- keep only the models whose lead block (from a first pass) has <= 16 | > 16 | 20..28 | > 28 levels, tiled to n")
     ap.add_argument("--same", type=int, default=-1, help="debug: every model is a copy of draw #SAME (I-cache experiments)")
     ap.add_argument("--kernel", type=int, default=0, help="rb_opts.kernel: 0 default, 1 v1 LU, 2 v2 without caching, 3 single launch, 4 without the half-warp engine")
     args = ap.parse_args()
@@ -217,14 +217,14 @@ def main():
         o = np.argsort(top, kind="stable")
         tk, nh2, cd, dens = tk[o].copy(), nh2[o].copy(), cd[o].copy(), dens[o].copy()
         d_tk.copy_(torch.from_numpy(tk)); d_cd.copy_(torch.from_numpy(cd)); d_dens.copy_(torch.from_numpy(dens))
-    if args.keep in ("small", "big"):
+    if args.keep in ("small", "big", "k57", "k8"):
         launch()
         torch.cuda.synchronize(dev)
         tau = d_tau.cpu().numpy()
         thick = ~(np.abs(tau) * 0.5 < np.float32(0.01))
         top = np.where(thick.any(axis=1), thick.shape[1] - np.argmax(thick[:, ::-1], axis=1), -1)   # upper level of the highest thick line
         key = np.maximum(3, (top + 1 + 4) >> 2)
-        sel = np.nonzero(key <= 4 if args.keep == "small" else key > 4)[0]
+        sel = np.nonzero({"small": key <= 4, "big": key > 4, "k57": (key > 4) & (key < 8), "k8": key >= 8}[args.keep])[0]
         o = np.resize(sel, n)
         tk, nh2, cd, dens = tk[o].copy(), nh2[o].copy(), cd[o].copy(), dens[o].copy()
         d_tk.copy_(torch.from_numpy(tk)); d_cd.copy_(torch.from_numpy(cd)); d_dens.copy_(torch.from_numpy(dens))

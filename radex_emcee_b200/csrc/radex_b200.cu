@@ -82,6 +82,8 @@ struct rb_ctx {
   void *sched_buf = nullptr;              // v2 scheduling: parked state, keys, order (grow-only)
   size_t sched_bytes = 0;
   unsigned long long *sched_small = nullptr;   // 64 words: histogram, offsets, cursors, parked count
+  cudaStream_t copy_stream = nullptr;     // host entry: results of one chunk travel while the next is solved
+  std::vector<cudaEvent_t> chunk_done;
   void *ln_buf = nullptr;                 // lnprob pipeline: model parameters, observed-line brightness, status (grow-only)
   size_t ln_bytes = 0;
   long long launches = 0;
@@ -1519,6 +1521,8 @@ void rb_ctx_destroy(rb_ctx *ctx) {
   if (ctx->sched_buf) cudaFree(ctx->sched_buf);
   if (ctx->sched_small) cudaFree(ctx->sched_small);
   if (ctx->ln_buf) cudaFree(ctx->ln_buf);
+  for (cudaEvent_t ev : ctx->chunk_done) cudaEventDestroy(ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -1596,9 +1600,12 @@ static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg, SolveIO io, c
   return RB_OK;
 }
 
-int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double *dens, const double *cdmol,
-                       double deltav_kms, double tbg, int geometry, const rb_opts *opts, double *xpop,
-                       double *tex, double *tau, double *surf, int32_t *niter, int32_t *status) {
+// keep_totals: a further chunk of one host call -- only the work-queue head is reset, the iteration total and the
+// cache statistics keep accumulating
+static int solve_batch_dev_impl(rb_ctx *ctx, int64_t n, const double *tkin, const double *dens, const double *cdmol,
+                                double deltav_kms, double tbg, int geometry, const rb_opts *opts, double *xpop,
+                                double *tex, double *tau, double *surf, int32_t *niter, int32_t *status,
+                                bool keep_totals) {
   int rc = check_common(ctx, deltav_kms, tbg, geometry);
   if (rc != RB_OK) return rc;
   if (n < 0 || (n > 0 && (!tkin || !dens || !cdmol))) {
@@ -1608,7 +1615,7 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
   if (n == 0) return RB_OK;
   CUDA_TRY(cudaSetDevice(ctx->device));
   const SolveCfg cfg = make_cfg(ctx, opts, deltav_kms, tbg, geometry);
-  CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, (keep_totals ? 1 : 8) * sizeof(unsigned long long), ctx->stream));
   SolveIO io{n, tkin, dens, cdmol, xpop, tex, tau, surf, niter, status, ctx->counters, 0, nullptr, nullptr, nullptr, nullptr};
   if (use_v2(ctx, opts)) {
     const Launch L = v2_launch(ctx, n);
@@ -1626,6 +1633,17 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
   ctx->launches += 1;
   return RB_OK;
 }
+
+int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double *dens, const double *cdmol,
+                       double deltav_kms, double tbg, int geometry, const rb_opts *opts, double *xpop,
+                       double *tex, double *tau, double *surf, int32_t *niter, int32_t *status) {
+  return solve_batch_dev_impl(ctx, n, tkin, dens, cdmol, deltav_kms, tbg, geometry, opts, xpop, tex, tau, surf, niter,
+                              status, false);
+}
+
+// Host-pointer entry.  Batches of more than 2 RB_HOST_CHUNK models are solved chunk by chunk, the results of one
+// chunk travelling to the host (copy stream) while the next one is being solved.
+#define RB_HOST_CHUNK (1LL << 18)
 
 int rb_solve_batch(rb_ctx *ctx, int64_t n, const double *tkin, const double *dens, const double *cdmol,
                    double deltav_kms, double tbg, int geometry, const rb_opts *opts, double *xpop, double *tex,
@@ -1661,14 +1679,45 @@ int rb_solve_batch(rb_ctx *ctx, int64_t n, const double *tkin, const double *den
   CUDA_TRY(cudaMemcpyAsync(d_t, tkin, n * sizeof(double), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(d_c, cdmol, n * sizeof(double), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(d_d, dens, (size_t)n * np * sizeof(double), cudaMemcpyHostToDevice, s));
-  rc = rb_solve_batch_dev(ctx, n, d_t, d_d, d_c, deltav_kms, tbg, geometry, opts, d_x, d_tex, d_tau, d_s, d_it, d_st);
+  const int64_t nchunk = (n > 2 * RB_HOST_CHUNK) ? (n + RB_HOST_CHUNK - 1) / RB_HOST_CHUNK : 1;
+  if (nchunk > 1 && !ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  while (nchunk > 1 && (int64_t)ctx->chunk_done.size() < nchunk) {
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->chunk_done.push_back(ev);
+  }
+  auto solve_chunk = [&](int64_t k) -> int {
+    const int64_t o = k * RB_HOST_CHUNK, m = std::min<int64_t>(RB_HOST_CHUNK, n - o);
+    if (nchunk == 1)
+      return solve_batch_dev_impl(ctx, n, d_t, d_d, d_c, deltav_kms, tbg, geometry, opts, d_x, d_tex, d_tau, d_s, d_it,
+                                  d_st, false);
+    return solve_batch_dev_impl(ctx, m, d_t + o, d_d + o * np, d_c + o, deltav_kms, tbg, geometry, opts,
+                                d_x ? d_x + o * nl : nullptr, d_tex ? d_tex + o * nn : nullptr,
+                                d_tau ? d_tau + o * nn : nullptr, d_s ? d_s + o * nn : nullptr, d_it + o, d_st + o, k > 0);
+  };
+  rc = solve_chunk(0);
   if (rc != RB_OK) return rc;
-  if (xpop) CUDA_TRY(cudaMemcpyAsync(xpop, d_x, (size_t)n * nl * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (tex) CUDA_TRY(cudaMemcpyAsync(tex, d_tex, (size_t)n * nn * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (tau) CUDA_TRY(cudaMemcpyAsync(tau, d_tau, (size_t)n * nn * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (surf) CUDA_TRY(cudaMemcpyAsync(surf, d_s, (size_t)n * nn * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (niter) CUDA_TRY(cudaMemcpyAsync(niter, d_it, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (status) CUDA_TRY(cudaMemcpyAsync(status, d_st, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  for (int64_t k = 0; k < nchunk; ++k) {
+    const int64_t o = (nchunk == 1) ? 0 : k * RB_HOST_CHUNK, m = (nchunk == 1) ? n : std::min<int64_t>(RB_HOST_CHUNK, n - o);
+    cudaStream_t cs = s;
+    if (nchunk > 1) {
+      // chunk k is queued: mark its end, queue chunk k + 1 behind it, then fetch chunk k on the copy stream
+      CUDA_TRY(cudaEventRecord(ctx->chunk_done[k], s));
+      if (k + 1 < nchunk) {
+        rc = solve_chunk(k + 1);
+        if (rc != RB_OK) return rc;
+      }
+      cs = ctx->copy_stream;
+      CUDA_TRY(cudaStreamWaitEvent(cs, ctx->chunk_done[k], 0));
+    }
+    if (xpop) CUDA_TRY(cudaMemcpyAsync(xpop + o * nl, d_x + o * nl, (size_t)m * nl * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    if (tex) CUDA_TRY(cudaMemcpyAsync(tex + o * nn, d_tex + o * nn, (size_t)m * nn * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    if (tau) CUDA_TRY(cudaMemcpyAsync(tau + o * nn, d_tau + o * nn, (size_t)m * nn * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    if (surf) CUDA_TRY(cudaMemcpyAsync(surf + o * nn, d_s + o * nn, (size_t)m * nn * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    if (niter) CUDA_TRY(cudaMemcpyAsync(niter + o, d_it + o, m * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status + o, d_st + o, m * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+  }
+  if (nchunk > 1) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
   unsigned long long cnt[3] = {0, 0, 0};
   CUDA_TRY(cudaMemcpyAsync(cnt, ctx->counters, sizeof(cnt), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));

@@ -264,6 +264,23 @@ def test_ordered_launches_without_half_warp_engine_are_bit_identical(ctx):
                 np.testing.assert_array_equal(a[k], ref[k], err_msg="%s %s kernel %d" % (k, kw, kernel))
 
 
+def test_chunked_host_entry(ctx):
+    """rb_solve_batch with host buffers solves batches of more than 2 x 2^18 models chunk by chunk, copying one
+    chunk's results back while the next is solved: same numbers as direct calls on slices, totals accumulated."""
+    n = 2 * (1 << 18) + 5000
+    P = draw_params(np.random.default_rng(77), 4096, 10.926)
+    P = P[np.arange(n) % 4096]
+    P[:, 0] *= 1.0 + 1e-7 * (np.arange(n) // 4096)      # distinct models, same population of cases
+    big = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926)
+    it_total, _ = ctx.counters()
+    ran = (big["status"] & 3) == 0
+    assert it_total == int(np.where(big["status"][ran] & 4, big["niter"][ran], big["niter"][ran] + 1).sum())
+    for sl in (slice(0, 9000), slice((1 << 18) - 4500, (1 << 18) + 4500), slice(n - 9000, n)):
+        part = gpu_solve(ctx, P[sl, 0], P[sl, 1], P[sl, 2], 10.926)
+        for k in ("xpop", "tex", "tau", "surf", "niter", "status"):
+            np.testing.assert_array_equal(big[k][sl], part[k], err_msg=k)
+
+
 def test_determinism(ctx):
     P = draw_params(np.random.default_rng(9), 200, 10.926)
     a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926)
