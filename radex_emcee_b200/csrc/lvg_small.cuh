@@ -19,7 +19,7 @@
 
 namespace v2s {
 
-using v2::LDB;
+using v2::MP;
 using v2::NL;
 using v2::ld2;
 using v2::st2;
@@ -123,7 +123,7 @@ __device__ __forceinline__ double lead_solve(double *sm, const int Kp, const int
     default: lead_pivots<11, 1>(q, rmine, pbase, vtb, hl);
   }
   __syncwarp();   // Vt complete
-  const int nf = NL - n, pitch = LDB - n;   // 29 or 25 frozen levels: lane hl owns n + hl and n + 16 + hl
+  const int nf = NL - n, pitch = MP - n;   // 29 or 25 frozen levels: lane hl owns n + hl and n + 16 + hl
   const double *vt = vtb + hl * (hl - 1) / 2;
   const bool two = hl + 16 < nf;
   const double *Mc1 = sm + S_M + hl, *Mc2 = sm + S_M + (two ? hl + 16 : 0);

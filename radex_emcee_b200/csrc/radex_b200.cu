@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(VS_WARPS * 32, 1) k_lvg_small(MolDev mol, Solv
       }
       nthick = (int)(packed & 0xffffffffLL);
       topthick = (int)(packed >> 32);
-      const int nlead = n * (n + 2), nm = n * (LDB - n);
+      const int nlead = n * (n + 2), nm = n * (MP - n);
       for (int e = hl; e < nlead; e += 16) sm[S_LEAD + e] = ex[EXT_LEAD + e];
       for (int e = hl; e < nm; e += 16) sm[S_M + e] = ex[EXT_LEAD + nlead + e];
       it = v2::IT_DECIDE;
