@@ -4,7 +4,8 @@
 // their cached iterations (lvg_v2.cuh: CACHED) eliminate a lead block of n = 12 or 16 levels with one row
 // per lane -- half of the warp idles, and the slab that has to stay on chip for them is 8.8 KB, not 19 KB.
 // This kernel runs those models two per warp (lanes 0-15 / 16-31, each half with its own slab and its own
-// iteration state), 24 models per SM instead of 12.  It contains NO full elimination: launch B captures the
+// iteration state), 26 (16 lead levels) or 32 (12 lead levels) models per SM instead of 12; one instantiation and
+// one launch per lead size, so the pivot loops are straight-line code with constant addresses.  It contains NO full elimination: launch B captures the
 // frozen top of such a model and parks lead block, response matrix and line bases (EXT_STRIDE doubles);
 // a model whose frozen lines turn thick is parked again and finished by launch C (v2::solve, sched = 4).
 //
@@ -28,23 +29,31 @@ using v2::KP_SMALL_MAX;               // lead blocks of 12 and 16 levels
 using v2::EXT_LEAD;
 using v2::EXT_STRIDE;
 constexpr int NROW_S = 4 * KP_SMALL_MAX;
-// ---- per-model shared-memory slab (doubles) ------------------------------------------------------------
-constexpr int S_LEAD = 0;            // lead block, row pitch n + 2                      (<= 16 x 18)
-constexpr int S_M = 288;             // M[i][f]: frozen populations from the lead ones, pitch 42 - n (<= 12 x 30, 16 x 26)
-constexpr int S_PB = S_M + 416;      // pivot-row broadcast buffers, 2 x 16 (1/s_k rides in slot K)
-constexpr int S_VT = S_PB + 32;      // raw pivot columns, triangular                    (<= 120)
-constexpr int S_X = S_VT + 120;      // relaxed populations
-constexpr int S_XNEW = S_X + 42;     // un-relaxed populations of this call
-constexpr int S_BETA = S_XNEW + 42;  // per line: escape probability of the call about to be made
-constexpr int S_DNB = S_BETA + 40;   //           non-radiative part of q[m][n] (collisions + Schur term)
-constexpr int S_UPB = S_DNB + 40;    //           non-radiative part of q[n][m]
-constexpr int S_TEX = S_UPB + 40;    //           excitation temperature
-constexpr int SSLAB = S_TEX + 40;    // 1100 doubles = 8800 B
-static_assert(SSLAB % 2 == 0, "slabs must stay 16 B aligned");
+// ---- per-model shared-memory slab (doubles), for a lead block of N = 4 KP levels -------------------------
+// KP = 3: 870 doubles (6960 B, 32 models = 16 warps per SM); KP = 4: 1100 doubles (8800 B, 26 models = 13 warps)
+template <int KP>
+struct Lay {
+  static constexpr int N = 4 * KP;
+  static constexpr int S_LEAD = 0;                    // lead block, row pitch N + 2
+  static constexpr int S_M = N * (N + 2);             // M[i][f]: frozen populations from the lead ones, pitch 42 - N
+  static constexpr int S_PB = S_M + N * (MP - N);     // pivot-row broadcast buffers, 2 x 16 (1/s_k rides in slot K)
+  static constexpr int S_VT = S_PB + 32;              // raw pivot columns, triangular
+  static constexpr int S_X = S_VT + N * (N - 1) / 2;  // relaxed populations
+  static constexpr int S_XNEW = S_X + 42;             // un-relaxed populations of this call
+  static constexpr int S_BETA = S_XNEW + 42;          // per line: escape probability of the call about to be made
+  static constexpr int S_DNB = S_BETA + 40;           //           non-radiative part of q[m][n] (collisions + Schur term)
+  static constexpr int S_UPB = S_DNB + 40;            //           non-radiative part of q[n][m]
+  static constexpr int S_TEX = S_UPB + 40;            //           excitation temperature
+  static constexpr int SSLAB = S_TEX + 40;
+  static constexpr int WARPS = (KP == 3) ? 16 : 13;   // 65536 registers / (128 x 32) = 16; shared memory: 227 KB
+  static_assert(SSLAB % 2 == 0 && S_M % 2 == 0 && S_PB % 2 == 0 && S_X % 2 == 0, "16 B alignment of the slab parts");
+};
 // ---- per-CTA constants (the same for every model of a call) --------------------------------------------
 constexpr int C_LA = 0, C_LGR = 40, C_LTDEN = 80, C_LECOEF = 120, C_LFKXNU = 160, C_LMN = 200, CSLAB = 220;
 // parked capture (global, per model; v2::EXT_STRIDE = 784 doubles): DNB[40] UPB[40] lead[n(n+2)] M[n(42-n)]
-static_assert(12 * 30 <= 416 && 16 * 26 <= 416, "response matrix overflows its region");
+static_assert(12 * 30 <= 416 && 16 * 26 <= 416, "response matrix overflows its slot in the parked capture");
+static_assert((CSLAB + 2 * Lay<3>::WARPS * Lay<3>::SSLAB) * 8 <= 232448 && (CSLAB + 2 * Lay<4>::WARPS * Lay<4>::SSLAB) * 8 <= 232448,
+              "slabs exceed the 227 KB of shared memory per CTA");
 
 __device__ __forceinline__ double half_sum(double v) {   // butterfly over the 16 lanes of a half-warp
 #pragma unroll
@@ -102,35 +111,32 @@ __device__ __forceinline__ void lead_pivots(double (&q)[NROW_S], double &rmine, 
   }
 }
 
-// v2::lead_solve for a half-warp; Kp (3 or 4) is the same in both halves of the warp.
-__device__ __forceinline__ double lead_solve(double *sm, const int Kp, const int hl) {
-  const int n = 4 * Kp;
-  double *B = sm + S_LEAD;
+// v2::lead_solve for a half-warp and a lead block of N = 4 KP levels (the same in both halves of the warp).
+template <int KP>
+__device__ __forceinline__ double lead_solve(double *sm, const int hl) {
+  using L = Lay<KP>;
+  constexpr int n = L::N;
+  double *B = sm + L::S_LEAD;
   double q[NROW_S];
   {
     const double *row = B + ((hl < n) ? hl : 0) * (n + 2);
 #pragma unroll
-    for (int j = 0; j < NROW_S; j += 4) {
-      if (j >= n) break;
+    for (int j = 0; j < n; j += 4) {
       const double2 a = ld2(row + j), b = ld2(row + j + 2);
       q[j] = a.x; q[j + 1] = a.y; q[j + 2] = b.x; q[j + 3] = b.y;
     }
   }
   double rmine = 0.0;
-  double *pbase = sm + S_PB, *vtb = sm + S_VT;
-  switch (Kp) {
-    case 4: lead_pivots<15, 12>(q, rmine, pbase, vtb, hl); [[fallthrough]];
-    default: lead_pivots<11, 1>(q, rmine, pbase, vtb, hl);
-  }
+  double *pbase = sm + L::S_PB, *vtb = sm + L::S_VT;
+  lead_pivots<n - 1, 1>(q, rmine, pbase, vtb, hl);
   __syncwarp();   // Vt complete
-  const int nf = NL - n, pitch = MP - n;   // 29 or 25 frozen levels: lane hl owns n + hl and n + 16 + hl
+  constexpr int nf = NL - n, pitch = MP - n;   // 29 or 25 frozen levels: lane hl owns n + hl and n + 16 + hl
   const double *vt = vtb + hl * (hl - 1) / 2;
   const bool two = hl + 16 < nf;
-  const double *Mc1 = sm + S_M + hl, *Mc2 = sm + S_M + (two ? hl + 16 : 0);
+  const double *Mc1 = sm + L::S_M + hl, *Mc2 = sm + L::S_M + (two ? hl + 16 : 0);
   double Y = 0.0, F1 = 0.0, F2 = 0.0, xi = 1.0, psum = 1.0, xmine = 1.0;
 #pragma unroll
-  for (int i = 0; i < NROW_S - 1; ++i) {
-    if (i >= n - 1) break;
+  for (int i = 0; i < n - 1; ++i) {
     Y = fma(xi, vt[i], Y);
     F1 = fma(xi, Mc1[i * pitch], F1);
     F2 = fma(xi, Mc2[i * pitch], F2);
@@ -140,9 +146,9 @@ __device__ __forceinline__ double lead_solve(double *sm, const int Kp, const int
   }
   F1 = fma(xi, Mc1[(n - 1) * pitch], F1);
   F2 = fma(xi, Mc2[(n - 1) * pitch], F2);
-  if (hl < n) sm[S_XNEW + hl] = xmine;
-  sm[S_XNEW + n + hl] = F1;
-  if (two) sm[S_XNEW + n + 16 + hl] = F2;
+  if (hl < n) sm[L::S_XNEW + hl] = xmine;
+  sm[L::S_XNEW + n + hl] = F1;
+  if (two) sm[L::S_XNEW + n + 16 + hl] = F2;
   // v2: psum + warp_sum(lane < nf ? F : 0): the first butterfly step pairs lane l with l + 16
   return psum + half_sum(F1 + (two ? F2 : 0.0));
 }

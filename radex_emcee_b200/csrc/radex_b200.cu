@@ -767,12 +767,12 @@ __global__ void k_sched_scatter(const int *keys, long long n, unsigned long long
 
 
 // ---- half-warp engine for small lead blocks (lvg_small.cuh): two models per warp, 24 per SM -----------------
-#ifndef VS_WARPS
-#define VS_WARPS 13
-#endif
-
-__global__ void __launch_bounds__(VS_WARPS * 32, 1) k_lvg_small(MolDev mol, SolveCfg cfg, SolveIO io) {
+template <int KP>
+__global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDev mol, SolveCfg cfg, SolveIO io) {
   using namespace v2s;
+  using L = Lay<KP>;
+  constexpr int SSLAB = L::SSLAB, S_LEAD = L::S_LEAD, S_M = L::S_M, S_X = L::S_X, S_XNEW = L::S_XNEW, S_BETA = L::S_BETA,
+                S_DNB = L::S_DNB, S_UPB = L::S_UPB, S_TEX = L::S_TEX;
   extern __shared__ double smem[];
   double *cs = smem;   // per-line constants of this call, shared by the CTA
   const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4, wib = threadIdx.x >> 5;
@@ -797,19 +797,20 @@ __global__ void __launch_bounds__(VS_WARPS * 32, 1) k_lvg_small(MolDev mol, Solv
   // a slab that never receives a model still runs the arithmetic of its warp: give it finite numbers
   for (int e = hl; e < SSLAB; e += 16) sm[e] = 1.0;
   __syncthreads();
-  // queue: positions [first of key 4, parked) of the sorted order; key 4 comes first, then key 3
-  const unsigned long long p_begin = io.sched_small[16 + 4], p3 = io.sched_small[16 + 3], p_end = io.sched_small[48];
+  // queue: the positions of key KP in the sorted order (heaviest key first; key 3 is the last block)
+  const unsigned long long p_begin = io.sched_small[16 + KP], p_end = io.sched_small[(KP == 3) ? 48 : 16 + KP - 1];
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-  bool active = false, pending = false, exhausted = false;
-  long long idx = 0, pidx = 0;
-  int Kp = 0, pKp = 0, it = 0, nthick = 0, topthick = -1;
+  bool active = false, exhausted = false, need_load = false;
+  long long idx = 0;
+  constexpr int Kp = KP, n = 4 * KP, pitch = n + 2;
+  int it = 0, nthick = 0, topthick = -1;
   unsigned flags = 0;   // bit t: line hl + 16 t had tau > 0.01f after the last call (RADEX's own stop rule)
   double cdmol = 1.0, cddv = 1.0;
   unsigned long long iters = 0, n_cached = 0, n_models = 0, n_inval = 0;
   for (;;) {
-    // ---- a free half takes the next model of the queue; it starts once its partner runs the same lead size --
-    if (!active && !pending && !exhausted) {
+    // ---- a free half takes the next model of the queue -------------------------------------------------------------
+    if (!active && !exhausted) {
       unsigned long long t = 0;
       if (hl == 0) t = atomicAdd(&io.counters[0], 1ULL);
       t = __shfl_sync(hmask, t, 0, 16);
@@ -817,23 +818,14 @@ __global__ void __launch_bounds__(VS_WARPS * 32, 1) k_lvg_small(MolDev mol, Solv
       if (pos >= p_end) {
         exhausted = true;
       } else {
-        pending = true;
-        pidx = io.order[pos];
-        pKp = (pos < p3) ? 4 : 3;
+        idx = io.order[pos];
+        active = need_load = true;
       }
     }
     __syncwarp();
-    const int a_kp = active ? Kp : 0, p_kp = pending ? pKp : 0;
-    const int a0 = __shfl_sync(0xffffffffu, a_kp, 0), a1 = __shfl_sync(0xffffffffu, a_kp, 16);
-    const int q0 = __shfl_sync(0xffffffffu, p_kp, 0), q1 = __shfl_sync(0xffffffffu, p_kp, 16);
-    const int wKp = a0 ? a0 : (a1 ? a1 : (q0 ? q0 : q1));
-    if (wKp == 0) break;   // nothing running, nothing waiting: the queue is empty
-    const int n = 4 * wKp, pitch = n + 2;
-    if (!active && pending && pKp == wKp) {
-      idx = pidx;
-      Kp = pKp;
-      pending = false;
-      active = true;
+    if (!__any_sync(0xffffffffu, active)) break;   // nothing running and the queue is empty
+    if (need_load) {
+      need_load = false;
       const double *st = io.state + idx * v2::STATE_STRIDE;
       const double *ex = io.ext + idx * EXT_STRIDE;
       for (int i = hl; i < NL; i += 16) sm[S_X + i] = st[i];
@@ -878,7 +870,7 @@ __global__ void __launch_bounds__(VS_WARPS * 32, 1) k_lvg_small(MolDev mol, Solv
       }
     }
     __syncwarp();
-    const double tot = lead_solve(sm, wKp, hl);
+    const double tot = lead_solve<KP>(sm, hl);
     __syncwarp();
     const double rtot = v2::rcp1(tot);
     // ---- normalise, floor, under-relax + pyradex's stop test (v2::solve; lane l of 32 owned levels l and l + 32)
@@ -1029,6 +1021,9 @@ __global__ void __launch_bounds__(VS_WARPS * 32, 1) k_lvg_small(MolDev mol, Solv
     }
   }
 }
+
+template <int KP>
+constexpr size_t small_smem() { return (size_t)(v2s::CSLAB + 2 * v2s::Lay<KP>::WARPS * v2s::Lay<KP>::SSLAB) * sizeof(double); }
 
 template <int NCOMP>
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lnprob_v2(MolDev mol, SolveCfg cfg, LnprobIO io) {
@@ -1491,8 +1486,9 @@ int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
       const int sm2 = (int)(V2_WARPS * v2::SLAB * sizeof(double));
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_solve_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_lvg_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)((v2s::CSLAB + 2 * VS_WARPS * v2s::SSLAB) * sizeof(double)));
+        e = cudaFuncSetAttribute(k_lvg_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<3>());
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_lvg_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<4>());
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess)
@@ -1584,16 +1580,17 @@ static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg, SolveIO io, c
   io.n_parked = ctx->sched_small + (small ? 16 + v2::KP_SMALL_MAX : 48);
   k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
   if (small) {
-    const size_t sm_s = (size_t)(v2s::CSLAB + 2 * VS_WARPS * v2s::SSLAB) * sizeof(double);
     CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
-    k_lvg_small<<<ctx->sm_count, VS_WARPS * 32, sm_s, ctx->stream>>>(ctx->mol, cfg, io);
+    k_lvg_small<4><<<ctx->sm_count, v2s::Lay<4>::WARPS * 32, small_smem<4>(), ctx->stream>>>(ctx->mol, cfg, io);
+    CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+    k_lvg_small<3><<<ctx->sm_count, v2s::Lay<3>::WARPS * 32, small_smem<3>(), ctx->stream>>>(ctx->mol, cfg, io);
     CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
     io.sched = 4;
     io.order = io.order_c;
     io.n_parked = ctx->sched_small + 49;
     io.ext = nullptr;
     k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
-    ctx->launches += 2;
+    ctx->launches += 3;
   }
   ctx->launches += 4;
   CUDA_TRY(cudaGetLastError());
