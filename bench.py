@@ -313,7 +313,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "models_per_gpu": n, "l2": "256 MiB flush write between timed steps",
                        "outputs": "xpop,tex,tau,surf,niter,status",
-                       "kernel": {0: "k_lvg_solve_v2 launches A, B, C (frozen-top caching, ordered by lead-block size) + k_lvg_small (half-warp engine for lead blocks <= 16 levels)",
+                       "kernel": {0: "k_lvg_solve_v2 launches A, B, C (frozen-top caching, ordered by lead-block size) + k_lvg_small<3..7> (cached engines per lead-block size, two models per warp up to 16 levels)",
                                   1: "k_lvg_solve_v1", 2: "k_lvg_solve_v2 (no caching)",
                                   3: "k_lvg_solve_v2 (frozen-top caching, single launch)",
                                   4: "k_lvg_solve_v2 (frozen-top caching, two launches ordered by lead-block size)"}[args.kernel]},

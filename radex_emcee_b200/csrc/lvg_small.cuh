@@ -1,4 +1,5 @@
-// lvg_small.cuh -- the cached engine of lvg_v2.cuh for SMALL lead blocks, one HALF-WARP per model.
+// lvg_small.cuh -- the cached engine of lvg_v2.cuh as kernels of its own, one instantiation per lead-block size:
+// one HALF-WARP per model for lead blocks of 12/16 levels, one warp per model for 20/24/28.
 //
 // In the forward sweep three quarters of the models keep every optically thick line below level 16, so
 // their cached iterations (lvg_v2.cuh: CACHED) eliminate a lead block of n = 12 or 16 levels with one row
@@ -18,6 +19,16 @@
 // by run_radex's loop (emcee/pyradex/core.py:856-925) for these models.
 #pragma once
 
+#ifndef V2S_WARPS5
+#define V2S_WARPS5 16
+#endif
+#ifndef V2S_WARPS6
+#define V2S_WARPS6 16
+#endif
+#ifndef V2S_WARPS7
+#define V2S_WARPS7 15
+#endif
+
 namespace v2s {
 
 using v2::MP;
@@ -28,16 +39,18 @@ using v2::st2;
 using v2::KP_SMALL_MAX;               // lead blocks of 12 and 16 levels
 using v2::EXT_LEAD;
 using v2::EXT_STRIDE;
-constexpr int NROW_S = 4 * KP_SMALL_MAX;
 // ---- per-model shared-memory slab (doubles), for a lead block of N = 4 KP levels -------------------------
 // KP = 3: 870 doubles (6960 B, 32 models = 16 warps per SM); KP = 4: 1100 doubles (8800 B, 26 models = 13 warps)
 template <int KP>
 struct Lay {
   static constexpr int N = 4 * KP;
+  static constexpr int G = (KP <= 4) ? 16 : 32;       // lanes per model: a half-warp up to 16 lead levels, else a warp
+  static constexpr int MPW = 32 / G;                  // models per warp
+  static constexpr int NT = (v2::MAXLINE + G - 1) / G;   // trips over the lines
   static constexpr int S_LEAD = 0;                    // lead block, row pitch N + 2
   static constexpr int S_M = N * (N + 2);             // M[i][f]: frozen populations from the lead ones, pitch 42 - N
-  static constexpr int S_PB = S_M + N * (MP - N);     // pivot-row broadcast buffers, 2 x 16 (1/s_k rides in slot K)
-  static constexpr int S_VT = S_PB + 32;              // raw pivot columns, triangular
+  static constexpr int S_PB = S_M + N * (MP - N);     // pivot-row broadcast buffers, 2 x G (1/s_k rides in slot K)
+  static constexpr int S_VT = S_PB + 2 * G;           // raw pivot columns, triangular
   static constexpr int S_X = S_VT + N * (N - 1) / 2;  // relaxed populations
   static constexpr int S_XNEW = S_X + 42;             // un-relaxed populations of this call
   static constexpr int S_BETA = S_XNEW + 42;          // per line: escape probability of the call about to be made
@@ -45,51 +58,57 @@ struct Lay {
   static constexpr int S_UPB = S_DNB + 40;            //           non-radiative part of q[n][m]
   static constexpr int S_TEX = S_UPB + 40;            //           excitation temperature
   static constexpr int SSLAB = S_TEX + 40;
-  static constexpr int WARPS = (KP == 3) ? 16 : 13;   // 65536 registers / (128 x 32) = 16; shared memory: 227 KB
+  // warps per CTA: bounded by the 227 KB of shared memory and by 65536 registers / (32 x registers per thread)
+  static constexpr int WARPS = (KP == 3) ? 16 : (KP == 4) ? 13 : (KP == 5) ? V2S_WARPS5 : (KP == 6) ? V2S_WARPS6 : V2S_WARPS7;
   static_assert(SSLAB % 2 == 0 && S_M % 2 == 0 && S_PB % 2 == 0 && S_X % 2 == 0, "16 B alignment of the slab parts");
 };
 // ---- per-CTA constants (the same for every model of a call) --------------------------------------------
 constexpr int C_LA = 0, C_LGR = 40, C_LTDEN = 80, C_LECOEF = 120, C_LFKXNU = 160, C_LMN = 200, CSLAB = 220;
 // parked capture (global, per model; v2::EXT_STRIDE = 784 doubles): DNB[40] UPB[40] lead[n(n+2)] M[n(42-n)]
-static_assert(12 * 30 <= 416 && 16 * 26 <= 416, "response matrix overflows its slot in the parked capture");
-static_assert((CSLAB + 2 * Lay<3>::WARPS * Lay<3>::SSLAB) * 8 <= 232448 && (CSLAB + 2 * Lay<4>::WARPS * Lay<4>::SSLAB) * 8 <= 232448,
+template <int KP>
+constexpr size_t smem_bytes() { return (size_t)(CSLAB + Lay<KP>::MPW * Lay<KP>::WARPS * Lay<KP>::SSLAB) * sizeof(double); }
+static_assert(smem_bytes<3>() <= 232448 && smem_bytes<4>() <= 232448 && smem_bytes<5>() <= 232448 &&
+                  smem_bytes<6>() <= 232448 && smem_bytes<7>() <= 232448,
               "slabs exceed the 227 KB of shared memory per CTA");
 
-__device__ __forceinline__ double half_sum(double v) {   // butterfly over the 16 lanes of a half-warp
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {   // butterfly over the G lanes of a model
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ int half_sum_int(int v) {
+template <int G>
+__device__ __forceinline__ int group_sum_int(int v) {
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ int half_max_int(int v) {
+template <int G>
+__device__ __forceinline__ int group_max_int(int v) {
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = G / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 
-template <int LO, int HI>
-__device__ __forceinline__ double sum_range(const double (&q)[NROW_S]) {   // same association as v2::sum_range
+template <int LO, int HI, int NR>
+__device__ __forceinline__ double sum_range(const double (&q)[NR]) {   // same association as v2::sum_range
   if constexpr (HI - LO == 1) {
     return q[LO];
   } else {
     constexpr int MID = (LO + HI) / 2;
-    return sum_range<LO, MID>(q) + sum_range<MID, HI>(q);
+    return sum_range<LO, MID, NR>(q) + sum_range<MID, HI, NR>(q);
   }
 }
 
 // v2::lead_pivots with hl = lane within the half; both halves run the same pivot on their own block.
-template <int K, int LO>
-__device__ __forceinline__ void lead_pivots(double (&q)[NROW_S], double &rmine, double *pbase, double *vt,
+template <int K, int LO, int NR, int G>
+__device__ __forceinline__ void lead_pivots(double (&q)[NR], double &rmine, double *pbase, double *vt,
                                             const int hl) {
   if constexpr (K >= LO) {
-    const double s = sum_range<0, K>(q);
+    const double s = sum_range<0, K, NR>(q);
     const double rr = v2::rcp1(s);
     const double r = (s > 0.0) ? rr : 0.0;
-    double *pb = pbase + (K & 1) * 16;
+    double *pb = pbase + (K & 1) * G;
     if (hl == K) {
       rmine = r;
 #pragma unroll
@@ -107,17 +126,17 @@ __device__ __forceinline__ void lead_pivots(double (&q)[NROW_S], double &rmine, 
       q[j] = fma(wv, u.x, q[j]);
       if (j + 1 < K) q[j + 1] = fma(wv, u.y, q[j + 1]);
     }
-    lead_pivots<K - 1, LO>(q, rmine, pbase, vt, hl);
+    lead_pivots<K - 1, LO, NR, G>(q, rmine, pbase, vt, hl);
   }
 }
 
-// v2::lead_solve for a half-warp and a lead block of N = 4 KP levels (the same in both halves of the warp).
+// v2::lead_solve for the G lanes of one model and a lead block of N = 4 KP levels.
 template <int KP>
 __device__ __forceinline__ double lead_solve(double *sm, const int hl) {
   using L = Lay<KP>;
-  constexpr int n = L::N;
+  constexpr int n = L::N, G = L::G;
   double *B = sm + L::S_LEAD;
-  double q[NROW_S];
+  double q[n];
   {
     const double *row = B + ((hl < n) ? hl : 0) * (n + 2);
 #pragma unroll
@@ -128,29 +147,31 @@ __device__ __forceinline__ double lead_solve(double *sm, const int hl) {
   }
   double rmine = 0.0;
   double *pbase = sm + L::S_PB, *vtb = sm + L::S_VT;
-  lead_pivots<n - 1, 1>(q, rmine, pbase, vtb, hl);
+  lead_pivots<n - 1, 1, n, G>(q, rmine, pbase, vtb, hl);
   __syncwarp();   // Vt complete
-  constexpr int nf = NL - n, pitch = MP - n;   // 29 or 25 frozen levels: lane hl owns n + hl and n + 16 + hl
-  const double *vt = vtb + hl * (hl - 1) / 2;
-  const bool two = hl + 16 < nf;
-  const double *Mc1 = sm + L::S_M + hl, *Mc2 = sm + L::S_M + (two ? hl + 16 : 0);
+  // frozen levels: lane hl owns n + hl and, in a half-warp (29 or 25 of them), n + 16 + hl
+  constexpr int nf = NL - n, pitch = MP - n;
+  const double *vt = vtb + ((hl < n) ? hl * (hl - 1) / 2 : 0);   // lanes >= n only go through the motions: stay inside the slab
+  const bool one = hl < nf, two = (G == 16) && (hl + 16 < nf);
+  const double *Mc1 = sm + L::S_M + (one ? hl : 0), *Mc2 = sm + L::S_M + (two ? hl + 16 : 0);
   double Y = 0.0, F1 = 0.0, F2 = 0.0, xi = 1.0, psum = 1.0, xmine = 1.0;
 #pragma unroll
   for (int i = 0; i < n - 1; ++i) {
     Y = fma(xi, vt[i], Y);
     F1 = fma(xi, Mc1[i * pitch], F1);
-    F2 = fma(xi, Mc2[i * pitch], F2);
-    xi = __shfl_sync(0xffffffffu, rmine * Y, i + 1, 16);
+    if (G == 16) F2 = fma(xi, Mc2[i * pitch], F2);
+    xi = __shfl_sync(0xffffffffu, rmine * Y, i + 1, G);
     psum += xi;
     xmine = (hl == i + 1) ? xi : xmine;
   }
   F1 = fma(xi, Mc1[(n - 1) * pitch], F1);
-  F2 = fma(xi, Mc2[(n - 1) * pitch], F2);
+  if (G == 16) F2 = fma(xi, Mc2[(n - 1) * pitch], F2);
   if (hl < n) sm[L::S_XNEW + hl] = xmine;
-  sm[L::S_XNEW + n + hl] = F1;
+  if (one) sm[L::S_XNEW + n + hl] = F1;
   if (two) sm[L::S_XNEW + n + 16 + hl] = F2;
-  // v2: psum + warp_sum(lane < nf ? F : 0): the first butterfly step pairs lane l with l + 16
-  return psum + half_sum(F1 + (two ? F2 : 0.0));
+  // v2: psum + warp_sum(lane < nf ? F : 0); in a half-warp the first butterfly step pairs lane l with l + 16
+  if (G == 16) return psum + group_sum<G>(F1 + (two ? F2 : 0.0));
+  return psum + group_sum<G>(one ? F1 : 0.0);
 }
 
 }  // namespace v2s

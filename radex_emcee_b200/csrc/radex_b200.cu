@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -62,7 +63,8 @@ struct SolveCfg {
   double abs_tol, fk_epi, thc_epi;
   int cache;                    // v2: frozen-top caching enabled (rb_opts.kernel != 2)
   int sched;                    // v2: launch scheduling allowed (rb_opts.kernel == 0 or 4)
-  int small;                    // v2: half-warp engine for lead blocks <= 16 levels (lvg_small.cuh; kernel == 0)
+  int small;                    // v2: cached engines as kernels of their own (lvg_small.cuh; kernel == 0)
+  int park_max;                 // v2: largest lead block (in panels) handed to them: 4 (half-warp engines only) or 7
   unsigned long long *stats;    // v2: [0] cached iterations, [1] captures, [2] invalidations
 };
 
@@ -766,18 +768,19 @@ __global__ void k_sched_scatter(const int *keys, long long n, unsigned long long
 }
 
 
-// ---- half-warp engine for small lead blocks (lvg_small.cuh): two models per warp, 24 per SM -----------------
+// ---- cached engines per lead-block size (lvg_small.cuh): G = 16 lanes per model up to 16 lead levels, else 32 ----
 template <int KP>
 __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDev mol, SolveCfg cfg, SolveIO io) {
   using namespace v2s;
   using L = Lay<KP>;
+  constexpr int G = L::G, NT = L::NT;
   constexpr int SSLAB = L::SSLAB, S_LEAD = L::S_LEAD, S_M = L::S_M, S_X = L::S_X, S_XNEW = L::S_XNEW, S_BETA = L::S_BETA,
                 S_DNB = L::S_DNB, S_UPB = L::S_UPB, S_TEX = L::S_TEX;
   extern __shared__ double smem[];
   double *cs = smem;   // per-line constants of this call, shared by the CTA
-  const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4, wib = threadIdx.x >> 5;
-  const unsigned hmask = 0xffffu << (16 * half);
-  double *sm = smem + CSLAB + (size_t)(2 * wib + half) * SSLAB;
+  const int lane = threadIdx.x & 31, hl = lane & (G - 1), half = lane / G, wib = threadIdx.x >> 5;
+  const unsigned hmask = (G == 32) ? 0xffffffffu : 0xffffu << (16 * half);   // the lanes of this model
+  double *sm = smem + CSLAB + (size_t)(L::MPW * wib + half) * SSLAB;
   int *lmn = reinterpret_cast<int *>(cs + C_LMN);
   const int nl = mol.nlev, nn = mol.nline;
   // the same expressions as the per-line set-up of v2::solve
@@ -795,7 +798,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     cs[C_LFKXNU + l] = RB_FK * xnu;
   }
   // a slab that never receives a model still runs the arithmetic of its warp: give it finite numbers
-  for (int e = hl; e < SSLAB; e += 16) sm[e] = 1.0;
+  for (int e = hl; e < SSLAB; e += G) sm[e] = 1.0;
   __syncthreads();
   // queue: the positions of key KP in the sorted order (heaviest key first; key 3 is the last block)
   const unsigned long long p_begin = io.sched_small[16 + KP], p_end = io.sched_small[(KP == 3) ? 48 : 16 + KP - 1];
@@ -813,7 +816,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     if (!active && !exhausted) {
       unsigned long long t = 0;
       if (hl == 0) t = atomicAdd(&io.counters[0], 1ULL);
-      t = __shfl_sync(hmask, t, 0, 16);
+      t = __shfl_sync(hmask, t, 0, G);
       const unsigned long long pos = p_begin + t;
       if (pos >= p_end) {
         exhausted = true;
@@ -828,13 +831,13 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
       need_load = false;
       const double *st = io.state + idx * v2::STATE_STRIDE;
       const double *ex = io.ext + idx * EXT_STRIDE;
-      for (int i = hl; i < NL; i += 16) sm[S_X + i] = st[i];
+      for (int i = hl; i < NL; i += G) sm[S_X + i] = st[i];
       const unsigned long long bits = reinterpret_cast<const unsigned long long *>(st)[121];
       const long long packed = reinterpret_cast<const long long *>(st)[122];
       flags = 0;
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        const int l = hl + 16 * t;
+      for (int t = 0; t < NT; ++t) {
+        const int l = hl + G * t;
         if (l < nn) {
           sm[S_TEX + l] = st[41 + l];
           sm[S_BETA + l] = st[81 + l];
@@ -846,8 +849,8 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
       nthick = (int)(packed & 0xffffffffLL);
       topthick = (int)(packed >> 32);
       const int nlead = n * (n + 2), nm = n * (MP - n);
-      for (int e = hl; e < nlead; e += 16) sm[S_LEAD + e] = ex[EXT_LEAD + e];
-      for (int e = hl; e < nm; e += 16) sm[S_M + e] = ex[EXT_LEAD + nlead + e];
+      for (int e = hl; e < nlead; e += G) sm[S_LEAD + e] = ex[EXT_LEAD + e];
+      for (int e = hl; e < nm; e += G) sm[S_M + e] = ex[EXT_LEAD + nlead + e];
       it = v2::IT_DECIDE;
       cdmol = io.cdmol[idx];
       cddv = cdmol / cfg.deltav_cms;
@@ -857,8 +860,8 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     // ---- one call of matrix(): radiative rates of the lead lines, lead block, M -------------------------------
     double *B = sm + S_LEAD;
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const int l = hl + 16 * t;
+    for (int t = 0; t < NT; ++t) {
+      const int l = hl + G * t;
       if (l < nn) {
         const int m = lmn[l] & 0xff, nlo = (lmn[l] >> 8) & 0xff;
         if (max(m, nlo) < n) {
@@ -873,10 +876,11 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     const double tot = lead_solve<KP>(sm, hl);
     __syncwarp();
     const double rtot = v2::rcp1(tot);
-    // ---- normalise, floor, under-relax + pyradex's stop test (v2::solve; lane l of 32 owned levels l and l + 32)
+    // ---- normalise, floor, under-relax + pyradex's stop test (v2::solve: lane l of 32 owns levels l and l + 32;
+    // in a half-warp lane hl stands for lanes hl (dA) and hl + 16 (dB) of that warp)
     double dA = 0.0, dB = 0.0;
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
+    for (int t = 0; t < ((G == 16) ? 3 : 2); ++t) {
       const int i = hl + ((t == 0) ? 0 : (t == 1) ? 32 : 16);
       if (i < NL) {
         const double xn = fmax(RB_MINPOP, sm[S_XNEW + i] * rtot);
@@ -888,7 +892,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
         if (t == 2) dB += fabs(prev - xr); else dA += fabs(prev - xr);
       }
     }
-    const double diff = half_sum(dA + dB);
+    const double diff = (G == 16) ? group_sum<G>(dA + dB) : group_sum<G>(dA);
     __syncwarp();
     // ---- per line: Tex of this call, optical depth and escape probability of the next ------------------------
     double tsA = 0.0, tsB = 0.0;
@@ -897,9 +901,10 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     topthick = -1;
     unsigned nflags = 0;
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const int tt = (t == 0) ? 0 : (t == 1) ? 2 : 1;   // lines hl, hl + 32, hl + 16: the order of the 32-lane sums
-      const int l = hl + 16 * tt;
+    for (int t = 0; t < NT; ++t) {
+      // half-warp: lines hl, hl + 32 (tsA), hl + 16 (tsB): the order of the 32-lane sums
+      const int tt = (G == 16) ? ((t == 0) ? 0 : (t == 1) ? 2 : 1) : t;
+      const int l = hl + G * tt;
       if (l < nn) {
         const int mn = lmn[l];
         const int m = mn & 0xff, nlo = (mn >> 8) & 0xff;
@@ -910,7 +915,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
         double thistex = told;
         if (!floored) thistex = cs[C_LFKXNU + l] * v2::rcp1(v2::fast_log(xn * gr * v2::rcp1(xm)));
         if (cfg.stop_rule == RB_STOP_RADEX && ((flags >> tt) & 1u)) {
-          if (tt == 1) tsB += fabs((thistex - told) / thistex); else tsA += fabs((thistex - told) / thistex);
+          if (G == 16 && tt == 1) tsB += fabs((thistex - told) / thistex); else tsA += fabs((thistex - told) / thistex);
         }
         sm[S_TEX + l] = (it == 0) ? thistex : 0.5 * (thistex + told);
         const double tau = cddv * (sm[S_X + nlo] * gr - sm[S_X + m]) * cs[C_LTDEN + l];
@@ -921,12 +926,12 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
       }
     }
     flags = nflags;
-    topthick = half_max_int(topthick);
+    topthick = group_max_int<G>(topthick);
     bool stop;
     if (cfg.stop_rule == RB_STOP_RADEX) {
       int conv = 0;
-      nthick = half_sum_int(nthick);
-      const double tsum = half_sum(tsA + tsB);
+      nthick = group_sum_int<G>(nthick);
+      const double tsum = (G == 16) ? group_sum<G>(tsA + tsB) : group_sum<G>(tsA);
       if (it >= 10) {
         if (nthick_this == 0) conv = 1;
         else if (tsum / nthick_this < RB_F32(1.0e-6)) conv = 1;
@@ -948,17 +953,17 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     if (leave) {
       // a frozen line turned thick: park for launch C, which re-captures with a larger lead block
       double *st = io.state + idx * v2::STATE_STRIDE;
-      for (int i = hl; i < NL; i += 16) st[i] = sm[S_X + i];
+      for (int i = hl; i < NL; i += G) st[i] = sm[S_X + i];
       unsigned long long bits = 0;
 #pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        const int l = hl + 16 * t;
+      for (int t = 0; t < NT; ++t) {
+        const int l = hl + G * t;
         if (l < nn) {
           st[41 + l] = sm[S_TEX + l];
           st[81 + l] = sm[S_BETA + l];
         }
-        const unsigned b = (__ballot_sync(hmask, (flags >> t) & 1u) >> (16 * half)) & 0xffffu;
-        bits |= (unsigned long long)b << (16 * t);
+        const unsigned b = __ballot_sync(hmask, (flags >> t) & 1u);
+        bits |= (unsigned long long)((G == 32) ? b : (b >> (16 * half)) & 0xffffu) << (G * t);
       }
       if (hl == 0) {
         reinterpret_cast<unsigned long long *>(st)[121] = bits;
@@ -976,7 +981,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     // ---- results (k_lvg_solve_v2's epilogue) --------------------------------------------------------------------
     int nonfinite = 0;
     const int l_first = io.obs_surf ? ((hl < io.nobs) ? io.obs_line[hl] : nn) : hl;
-    const int l_step = io.obs_surf ? nn : 16;
+    const int l_step = io.obs_surf ? nn : G;
 #pragma unroll 1
     for (int l = l_first; l < nn; l += l_step) {
       const int m = lmn[l] & 0xff, nlo = (lmn[l] >> 8) & 0xff;
@@ -1001,7 +1006,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
       if (io.tau) io.tau[idx * nn + l] = tau;
     }
     if (io.xpop)
-      for (int i = hl; i < nl; i += 16) io.xpop[idx * nl + i] = sm[S_X + i];
+      for (int i = hl; i < nl; i += G) io.xpop[idx * nl + i] = sm[S_X + i];
     nonfinite = __any_sync(hmask, nonfinite);
     if (hl == 0) {
       if (io.niter) io.niter[idx] = it;
@@ -1016,14 +1021,14 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     if (iters) atomicAdd(&io.counters[1], iters);
     if (cfg.stats && n_models) {
       atomicAdd(&cfg.stats[0], n_cached);
-      atomicAdd(&cfg.stats[1], n_models);   // one capture each (made by launch B)
+      atomicAdd(&cfg.stats[1], n_models);   // one capture each (made by launch A)
       if (n_inval) atomicAdd(&cfg.stats[2], n_inval);
     }
   }
 }
 
 template <int KP>
-constexpr size_t small_smem() { return (size_t)(v2s::CSLAB + 2 * v2s::Lay<KP>::WARPS * v2s::Lay<KP>::SSLAB) * sizeof(double); }
+constexpr size_t small_smem() { return v2s::smem_bytes<KP>(); }
 
 template <int NCOMP>
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lnprob_v2(MolDev mol, SolveCfg cfg, LnprobIO io) {
@@ -1313,6 +1318,7 @@ SolveCfg make_cfg(const rb_ctx *ctx, const rb_opts *o, double deltav_kms, double
   c.cache = (d.kernel != 2);
   c.sched = (d.kernel == 0 || d.kernel == 4);
   c.small = (d.kernel == 0);
+  c.park_max = 4;
   c.stats = ctx->counters + 3;
   return c;
 }
@@ -1489,6 +1495,12 @@ int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
         e = cudaFuncSetAttribute(k_lvg_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<3>());
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_lvg_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<4>());
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_lvg_small<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<5>());
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_lvg_small<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<6>());
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_lvg_small<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<7>());
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
       if (e == cudaSuccess)
@@ -1543,9 +1555,15 @@ int rb_ctx_reset_stream(rb_ctx *ctx) {
 
 // The scheduled solve of a large batch (lvg_v2.cuh, lvg_small.cuh): launch A, counting sort by lead-block size,
 // launch B (large lead blocks), k_lvg_small (small ones, two per warp), launch C (invalidated small ones).
-static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg, SolveIO io, const Launch &L) {
+#define RB_MID_MIN (1LL << 18)   // batches from this size on also run the 20/24/28-level lead blocks in their own launches
+                                 // (measured: 2^17 models 3 % slower with the three extra launches and their tails, 2^18 2 % faster, 2^20 6 % faster)
+
+static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg_in, SolveIO io, const Launch &L) {
   const long long n = io.n;
-  const bool small = cfg.small != 0 && n <= (1LL << 21);   // the parked captures take 6.3 KB per model
+  SolveCfg cfg = cfg_in;
+  cfg.park_max = (n >= RB_MID_MIN) ? v2::KP_SMALL_MAX : 4;
+  if (const char *e = getenv("RB_PARK_MAX")) cfg.park_max = atoi(e);   // A/B aid
+  const bool small = cfg.small != 0 && n <= (1LL << 20);   // the parked captures take 10.9 KB per model
   const size_t b_state = align256((size_t)n * v2::STATE_STRIDE * sizeof(double)), b_int = align256((size_t)n * sizeof(int));
   const size_t b_ext = small ? align256((size_t)n * v2::EXT_STRIDE * sizeof(double)) : 0;
   const size_t b_all = b_state + (small ? 3 : 2) * b_int + b_ext;
@@ -1577,10 +1595,20 @@ static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg, SolveIO io, c
   io.sched = 2;
   io.order = order;
   // heaviest key first: with the half-warp engine launch B stops where key 4 begins
-  io.n_parked = ctx->sched_small + (small ? 16 + v2::KP_SMALL_MAX : 48);
+  io.n_parked = ctx->sched_small + (small ? 16 + cfg.park_max : 48);
   k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
   if (small) {
+    // one launch per lead-block size, heaviest first (each has its own block of the sorted order)
     CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+    if (cfg.park_max >= 7) {
+      k_lvg_small<7><<<ctx->sm_count, v2s::Lay<7>::WARPS * 32, small_smem<7>(), ctx->stream>>>(ctx->mol, cfg, io);
+      CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+      k_lvg_small<6><<<ctx->sm_count, v2s::Lay<6>::WARPS * 32, small_smem<6>(), ctx->stream>>>(ctx->mol, cfg, io);
+      CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+      k_lvg_small<5><<<ctx->sm_count, v2s::Lay<5>::WARPS * 32, small_smem<5>(), ctx->stream>>>(ctx->mol, cfg, io);
+      CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+      ctx->launches += 3;
+    }
     k_lvg_small<4><<<ctx->sm_count, v2s::Lay<4>::WARPS * 32, small_smem<4>(), ctx->stream>>>(ctx->mol, cfg, io);
     CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
     k_lvg_small<3><<<ctx->sm_count, v2s::Lay<3>::WARPS * 32, small_smem<3>(), ctx->stream>>>(ctx->mol, cfg, io);

@@ -3,6 +3,7 @@ by the reference binary.  Tolerances from BASELINE.json north_star: populations 
 within 1e-5 relative; compared on entries the reference itself resolves (population > 1e-9, lines
 whose flux is > 1e-6 of the model's brightest line)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -244,9 +245,9 @@ def test_two_launch_schedule_is_bit_identical(ctx):
 
 
 def test_ordered_launches_without_half_warp_engine_are_bit_identical(ctx):
-    """kernel=0 (the default, checked above) runs the models with lead blocks of <= 16 levels two per warp in
-    k_lvg_small (capture parked by launch A, invalidated models finished by launch C); kernel=4 is the
-    same ordering without that engine.  Both repeat the single launch (kernel=3) bit for bit, outputs,
+    """kernel=0 (the default, checked above) runs the cached iterations in k_lvg_small<KP>, one launch per
+    lead-block size, two models per warp up to 16 lead levels (capture parked by launch A, invalidated models
+    finished by launch C); kernel=4 is the same ordering without those engines.  Both repeat the single launch (kernel=3) bit for bit, outputs,
     iteration total and cache statistics."""
     P = draw_params(np.random.default_rng(34), 20000, 10.926)
     P[9, 0] = 2.0e4         # T out of range
@@ -255,13 +256,20 @@ def test_ordered_launches_without_half_warp_engine_are_bit_identical(ctx):
         ref = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, kernel=3, **kw)
         itr, _ = ctx.counters()
         sr = ctx.cache_stats()
-        for kernel in (0, 4):
-            a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, kernel=kernel, **kw)
+        # kernel 0 twice: half-warp engines only (batches < 2^18), then with the 20/24/28-level lead blocks in
+        # their own launches as well (forced here through the A/B switch RB_PARK_MAX)
+        for kernel, park_max in ((0, None), (0, "7"), (4, None)):
+            if park_max is not None:
+                os.environ["RB_PARK_MAX"] = park_max
+            try:
+                a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, kernel=kernel, **kw)
+            finally:
+                os.environ.pop("RB_PARK_MAX", None)
             ita, _ = ctx.counters()
-            assert ita == itr, (kernel, kw, ita, itr)
-            assert tuple(ctx.cache_stats()) == tuple(sr), (kernel, kw)
+            assert ita == itr, (kernel, park_max, kw, ita, itr)
+            assert tuple(ctx.cache_stats()) == tuple(sr), (kernel, park_max, kw)
             for k in ("xpop", "tex", "tau", "surf", "niter", "status"):
-                np.testing.assert_array_equal(a[k], ref[k], err_msg="%s %s kernel %d" % (k, kw, kernel))
+                np.testing.assert_array_equal(a[k], ref[k], err_msg="%s %s kernel %d park_max %s" % (k, kw, kernel, park_max))
 
 
 def test_chunked_host_entry(ctx):

@@ -15,6 +15,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 maxiter = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 ctx = _lib.Context(_lib.MolData(MOLFILE), 0)
 P = draw_params(np.random.default_rng(5), n, 10.926)
+os.environ["RB_PARK_MAX"] = "7"   # all five cached-engine kernels
 a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, maxiter=maxiter)
 b = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, maxiter=maxiter, kernel=3)
 for k in a:
