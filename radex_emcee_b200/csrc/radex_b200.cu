@@ -667,8 +667,9 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
 // ------------------------------------------------------------------------------------------------
 #define V2_WARPS 12
 #define RB_SCHED_MIN 8192   // batches smaller than this run as one launch
-#define RB_LNPROB_PIPE_MIN 16384   // walkers per call from which lnprob runs as a pipeline (measured: 2 components,
-                                   // 8192 walkers per call: fused launch 7 % faster; 1 component, 16384: pipeline 41 % faster)
+// walkers per call from which lnprob runs as a pipeline.  Measured (walker-steps/s, pipeline vs fused launch): 1 component,
+// 8192 walkers per call 4.35e6 vs 3.64e6; 2 components, 8192 per call 1.43e6 vs 1.65e6, 16384 per call 2.11e6 vs 1.80e6
+#define RB_LNPROB_PIPE_MIN(ncomp) ((ncomp) == 1 ? 8192 : 16384)
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, SolveCfg cfg, SolveIO io) {
   extern __shared__ double smem[];
@@ -1781,7 +1782,9 @@ static int lnprob_dev(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const 
   io.has_td = has_td;
   io.t_d = t_d;
   io.counters = ctx->counters;
-  if (use_v2(ctx, opts) && cfg.sched && cfg.small && cfg.cache && n >= RB_LNPROB_PIPE_MIN) {
+  long long pipe_min = RB_LNPROB_PIPE_MIN(ncomp);
+  if (const char *e = getenv("RB_LNPROB_PIPE_MIN")) pipe_min = atoll(e);   // A/B aid
+  if (use_v2(ctx, opts) && cfg.sched && cfg.small && cfg.cache && n >= pipe_min && n * ncomp >= RB_SCHED_MIN) {
     // large ensembles: expand -> scheduled solve of all n x ncomp models (half-warp engine) -> combine
     const long long m = n * ncomp;
     const int np = ctx->mol.npart;
