@@ -35,9 +35,9 @@ F_ITER = 72368.0
 F_PRO = 1.3e4
 F_EPI = 4.0e3
 # DRAM bytes of one 2^20 step (all launches), dram__bytes_read.sum + dram__bytes_write.sum of the ncu pass kept in
-# profiles/r1d_launches.csv (IDs 22-28): launch A 5.84 GB (parks 1 KB of state per model and 6.3 KB of capture per
-# small-lead model), B 0.92 GB, k_lvg_small 5.81 GB (reads them back, writes the results), C 0.08 GB
-TRAFFIC_NCU_2P20 = 12.66e9
+# profiles/r1e_launches.csv (IDs 34-44): launch A 8.65 GB (parks 1 KB of state per model and 10.9 KB of capture per
+# cacheable model), B 0.18 GB, the five cached-engine launches 8.4 GB (read them back, write the results), C 0.3 GB
+TRAFFIC_NCU_2P20 = 17.5e9
 
 
 def draw(n, seed):
@@ -329,7 +329,7 @@ def main():
                          "frac": achieved / fp64_peak,
                          "traffic": TRAFFIC_NCU_2P20 if (args.log2n == 20 and args.kernel == 0 and stop_rule == 0
                                                           and not args.keep and not args.sort and args.same < 0) else None,
-                         "traffic_unit": "bytes per step, all launches (ncu, profiles/r1d_launches.csv); algorithmic bytes = h2d + d2h",
+                         "traffic_unit": "bytes per step, all launches (ncu, profiles/r1e_launches.csv); algorithmic bytes = h2d + d2h",
                          "peak_source": "rb_fp64_peak DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 "
                                         "figure); nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2",
                          "flops_per_iter": F_ITER,
