@@ -1559,12 +1559,35 @@ int rb_ctx_reset_stream(rb_ctx *ctx) {
 #define RB_MID_MIN (1LL << 18)   // batches from this size on also run the 20/24/28-level lead blocks in their own launches
                                  // (measured: 2^17 models 3 % slower with the three extra launches and their tails, 2^18 2 % faster, 2^20 6 % faster)
 
+#define RB_PIPE_MAX (1LL << 20)   // models per scheduled pass: bounds the parked captures at 12.5 GB
+
 static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg_in, SolveIO io, const Launch &L) {
+  if (io.n > RB_PIPE_MAX && cfg_in.small) {   // larger batches: one pass per 2^20 models, totals keep accumulating
+    const int np = ctx->mol.npart, nl = ctx->mol.nlev, nn = ctx->mol.nline;
+    for (long long o = 0; o < io.n; o += RB_PIPE_MAX) {
+      SolveIO part = io;
+      part.n = std::min<long long>(RB_PIPE_MAX, io.n - o);
+      part.tkin += o;
+      part.dens += o * np;
+      part.cdmol += o;
+      if (part.xpop) part.xpop += o * nl;
+      if (part.tex) part.tex += o * nn;
+      if (part.tau) part.tau += o * nn;
+      if (part.surf) part.surf += o * nn;
+      if (part.niter) part.niter += o;
+      if (part.status) part.status += o;
+      if (part.obs_surf) part.obs_surf += o * RB_MAX_OBS;
+      if (o > 0) CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));   // queue head
+      const int rc = launch_solve_pipeline(ctx, cfg_in, part, v2_launch(ctx, part.n));
+      if (rc != RB_OK) return rc;
+    }
+    return RB_OK;
+  }
   const long long n = io.n;
   SolveCfg cfg = cfg_in;
   cfg.park_max = (n >= RB_MID_MIN) ? v2::KP_SMALL_MAX : 4;
   if (const char *e = getenv("RB_PARK_MAX")) cfg.park_max = atoi(e);   // A/B aid
-  const bool small = cfg.small != 0 && n <= (1LL << 20);   // the parked captures take 10.9 KB per model
+  const bool small = cfg.small != 0;   // the parked captures take 10.9 KB per model
   const size_t b_state = align256((size_t)n * v2::STATE_STRIDE * sizeof(double)), b_int = align256((size_t)n * sizeof(int));
   const size_t b_ext = small ? align256((size_t)n * v2::EXT_STRIDE * sizeof(double)) : 0;
   const size_t b_all = b_state + (small ? 3 : 2) * b_int + b_ext;

@@ -289,6 +289,43 @@ def test_chunked_host_entry(ctx):
             np.testing.assert_array_equal(big[k][sl], part[k], err_msg=k)
 
 
+def test_device_entry_above_one_pass(ctx):
+    """rb_solve_batch_dev schedules batches of more than 2^20 models in passes of 2^20 (the parked captures of one pass
+    take 12.5 GB): same numbers as direct calls on slices, iteration total accumulated over the passes."""
+    import torch
+    n = (1 << 20) + 6000
+    P = draw_params(np.random.default_rng(78), 4096, 10.926)
+    P = P[np.arange(n) % 4096]
+    P[:, 0] *= 1.0 + 1e-7 * (np.arange(n) // 4096)
+    mol = ctx.mol
+    dens = np.zeros((n, mol.npart))
+    for p, pid in enumerate(mol.partner_id):
+        dens[:, p] = {2: 0.25, 3: 0.75}.get(int(pid), 0.0) * P[:, 1]
+    dev = torch.device("cuda", 0)
+    d_t, d_d, d_c = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (P[:, 0], dens, P[:, 2]))
+    d_surf = torch.empty((n, mol.nline), dtype=torch.float64, device=dev)
+    d_it = torch.empty(n, dtype=torch.int32, device=dev)
+    d_st = torch.empty(n, dtype=torch.int32, device=dev)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        opts = _lib.default_opts()
+        _lib.check(_lib.load().rb_solve_batch_dev(ctx.handle, n, d_t.data_ptr(), d_d.data_ptr(), d_c.data_ptr(), 1.0, 10.926, 2,
+                                                  C.byref(opts), None, None, None, d_surf.data_ptr(), d_it.data_ptr(),
+                                                  d_st.data_ptr()))
+        torch.cuda.synchronize(dev)
+        it_total, _ = ctx.counters()
+    finally:
+        ctx.reset_stream()
+    surf, niter, status = d_surf.cpu().numpy(), d_it.cpu().numpy(), d_st.cpu().numpy()
+    ran = (status & 3) == 0
+    assert it_total == int(np.where(status[ran] & 4, niter[ran], niter[ran] + 1).sum())
+    for sl in (slice(0, 9000), slice((1 << 20) - 4500, (1 << 20) + 4500), slice(n - 9000, n)):
+        part = gpu_solve(ctx, P[sl, 0], P[sl, 1], P[sl, 2], 10.926)
+        np.testing.assert_array_equal(surf[sl], part["surf"])
+        np.testing.assert_array_equal(niter[sl], part["niter"])
+        np.testing.assert_array_equal(status[sl], part["status"])
+
+
 def test_determinism(ctx):
     P = draw_params(np.random.default_rng(9), 200, 10.926)
     a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926)
