@@ -84,6 +84,8 @@ struct rb_ctx {
   void *sched_buf = nullptr;              // v2 scheduling: parked state, keys, order (grow-only)
   size_t sched_bytes = 0;
   unsigned long long *sched_small = nullptr;   // 64 words: histogram, offsets, cursors, parked count
+  cudaStream_t side[6] = {};              // launch B and the five cached-engine launches run side by side (independent models)
+  cudaEvent_t ev_sorted = nullptr, ev_side[6] = {};
   cudaStream_t copy_stream = nullptr;     // host entry: results of one chunk travel while the next is solved
   std::vector<cudaEvent_t> chunk_done;
   void *ln_buf = nullptr;                 // lnprob pipeline: model parameters, observed-line brightness, status (grow-only)
@@ -494,6 +496,7 @@ struct SolveIO {
   double *ext;                         // n x v2s::EXT_STRIDE
   unsigned long long *sched_small;     // [16+k] first queue position of key k, [48] parked, [49] models for launch C
   int *order_c;
+  int queue;                           // work-queue head of this launch: counters[queue] (0, or 8.. when launches overlap)
 };
 
 __global__ void __launch_bounds__(256) k_lvg_solve_v1(MolDev mol, SolveCfg cfg, SolveIO io) {
@@ -667,9 +670,10 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
 // ------------------------------------------------------------------------------------------------
 #define V2_WARPS 12
 #define RB_SCHED_MIN 8192   // batches smaller than this run as one launch
-// walkers per call from which lnprob runs as a pipeline.  Measured (walker-steps/s, pipeline vs fused launch): 1 component,
-// 8192 walkers per call 4.35e6 vs 3.64e6; 2 components, 8192 per call 1.43e6 vs 1.65e6, 16384 per call 2.11e6 vs 1.80e6
-#define RB_LNPROB_PIPE_MIN(ncomp) ((ncomp) == 1 ? 8192 : 16384)
+// walkers per call from which lnprob runs as a pipeline.  Measured (walker-steps/s, pipeline vs fused launch, with launch B
+// and the engine launches overlapping): 1 component, 8192 walkers per call 4.35e6 vs 3.64e6; 2 components, 8192 per call
+// 1.86e6 vs 1.66e6, 16384 per call 2.49e6 vs 1.80e6
+#define RB_LNPROB_PIPE_MIN(ncomp) 8192
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, SolveCfg cfg, SolveIO io) {
   extern __shared__ double smem[];
@@ -684,7 +688,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
   const long long limit = (io.sched >= 2) ? (long long)*io.n_parked : io.n;
   for (;;) {
     unsigned long long idx = 0;
-    if (lane == 0) idx = atomicAdd(&io.counters[0], 1ULL);
+    if (lane == 0) idx = atomicAdd(&io.counters[io.queue], 1ULL);
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if ((long long)idx >= limit) break;
     if (io.sched >= 2) idx = (unsigned long long)io.order[idx];
@@ -816,7 +820,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     // ---- a free half takes the next model of the queue -------------------------------------------------------------
     if (!active && !exhausted) {
       unsigned long long t = 0;
-      if (hl == 0) t = atomicAdd(&io.counters[0], 1ULL);
+      if (hl == 0) t = atomicAdd(&io.counters[io.queue], 1ULL);
       t = __shfl_sync(hmask, t, 0, G);
       const unsigned long long pos = p_begin + t;
       if (pos >= p_end) {
@@ -1480,7 +1484,7 @@ int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
     UP(pt.rates_tc, m.rates_tc[p]);
   }
 #undef UP
-  if (rc == RB_OK && cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+  if (rc == RB_OK && cudaMalloc(&ctx->counters, 16 * sizeof(unsigned long long)) != cudaSuccess) {
     rb_set_error("cudaMalloc(counters) failed");
     rc = RB_ERR_CUDA;
   }
@@ -1531,6 +1535,11 @@ void rb_ctx_destroy(rb_ctx *ctx) {
   if (ctx->sched_small) cudaFree(ctx->sched_small);
   if (ctx->ln_buf) cudaFree(ctx->ln_buf);
   for (cudaEvent_t ev : ctx->chunk_done) cudaEventDestroy(ev);
+  for (int j = 0; j < 6; ++j) {
+    if (ctx->side[j]) cudaStreamDestroy(ctx->side[j]);
+    if (ctx->ev_side[j]) cudaEventDestroy(ctx->ev_side[j]);
+  }
+  if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -1556,9 +1565,9 @@ int rb_ctx_reset_stream(rb_ctx *ctx) {
 
 // The scheduled solve of a large batch (lvg_v2.cuh, lvg_small.cuh): launch A, counting sort by lead-block size,
 // launch B (large lead blocks), k_lvg_small (small ones, two per warp), launch C (invalidated small ones).
-#define RB_MID_MIN (1LL << 18)   // batches from this size on also run the 20/24/28-level lead blocks in their own launches
-                                 // (measured: 2^17 models 3 % slower with the three extra launches and their tails, 2^18 2 % faster, 2^20 6 % faster)
-
+#define RB_MID_MIN (1LL << 17)   // batches from this size on also run the 20/24/28-level lead blocks in their own launches
+                                 // (measured with the launches overlapping: 2^16 models 4 % slower with the three extra
+                                 // launches, 2^17 2 % faster, 2^20 6 % faster)
 #define RB_PIPE_MAX (1LL << 20)   // models per scheduled pass: bounds the parked captures at 12.5 GB
 
 static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg_in, SolveIO io, const Launch &L) {
@@ -1615,34 +1624,51 @@ static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg_in, SolveIO io
   k_sched_hist<<<nb, tpb, 0, ctx->stream>>>(io.keys, n, ctx->sched_small);
   k_sched_scan<<<1, 1, 0, ctx->stream>>>(ctx->sched_small);
   k_sched_scatter<<<nb, tpb, 0, ctx->stream>>>(io.keys, n, ctx->sched_small, order);
-  CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));   // queue head only
   io.sched = 2;
   io.order = order;
-  // heaviest key first: with the half-warp engine launch B stops where key 4 begins
+  // heaviest key first: with the cached engines in kernels of their own launch B stops where their keys begin
   io.n_parked = ctx->sched_small + (small ? 16 + cfg.park_max : 48);
-  k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
-  if (small) {
-    // one launch per lead-block size, heaviest first (each has its own block of the sorted order)
-    CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
-    if (cfg.park_max >= 7) {
-      k_lvg_small<7><<<ctx->sm_count, v2s::Lay<7>::WARPS * 32, small_smem<7>(), ctx->stream>>>(ctx->mol, cfg, io);
-      CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
-      k_lvg_small<6><<<ctx->sm_count, v2s::Lay<6>::WARPS * 32, small_smem<6>(), ctx->stream>>>(ctx->mol, cfg, io);
-      CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
-      k_lvg_small<5><<<ctx->sm_count, v2s::Lay<5>::WARPS * 32, small_smem<5>(), ctx->stream>>>(ctx->mol, cfg, io);
-      CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
-      ctx->launches += 3;
+  if (!small) {
+    CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));   // queue head only
+    k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
+  } else {
+    // Launch B and the engine launches work on disjoint models: each gets its own stream and queue head, so the
+    // tail of one (SMs idling while its last models finish their <= 200 calls) is filled by the CTAs of the next.
+    cudaStream_t s = ctx->stream;
+    if (!ctx->ev_sorted) {
+      CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming));
+      for (int j = 0; j < 6; ++j) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side[j], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_side[j], cudaEventDisableTiming));
+      }
     }
-    k_lvg_small<4><<<ctx->sm_count, v2s::Lay<4>::WARPS * 32, small_smem<4>(), ctx->stream>>>(ctx->mol, cfg, io);
-    CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
-    k_lvg_small<3><<<ctx->sm_count, v2s::Lay<3>::WARPS * 32, small_smem<3>(), ctx->stream>>>(ctx->mol, cfg, io);
-    CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->counters + 8, 0, 8 * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaEventRecord(ctx->ev_sorted, s));
+    for (int j = 0; j < 6; ++j) {
+      if (j >= 1 && j <= 3 && cfg.park_max < 7) continue;   // keys 7, 6, 5 stay in launch B for small batches
+      cudaStream_t sj = ctx->side[j];
+      CUDA_TRY(cudaStreamWaitEvent(sj, ctx->ev_sorted, 0));
+      io.queue = 8 + j;
+      switch (j) {
+        case 0: k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, sj>>>(ctx->mol, cfg, io); break;
+        case 1: k_lvg_small<7><<<ctx->sm_count, v2s::Lay<7>::WARPS * 32, small_smem<7>(), sj>>>(ctx->mol, cfg, io); break;
+        case 2: k_lvg_small<6><<<ctx->sm_count, v2s::Lay<6>::WARPS * 32, small_smem<6>(), sj>>>(ctx->mol, cfg, io); break;
+        case 3: k_lvg_small<5><<<ctx->sm_count, v2s::Lay<5>::WARPS * 32, small_smem<5>(), sj>>>(ctx->mol, cfg, io); break;
+        case 4: k_lvg_small<4><<<ctx->sm_count, v2s::Lay<4>::WARPS * 32, small_smem<4>(), sj>>>(ctx->mol, cfg, io); break;
+        default: k_lvg_small<3><<<ctx->sm_count, v2s::Lay<3>::WARPS * 32, small_smem<3>(), sj>>>(ctx->mol, cfg, io); break;
+      }
+      CUDA_TRY(cudaEventRecord(ctx->ev_side[j], sj));
+      CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_side[j], 0));
+      ctx->launches += (j > 0);
+    }
+    io.queue = 0;
+    CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), s));
     io.sched = 4;
     io.order = io.order_c;
     io.n_parked = ctx->sched_small + 49;
     io.ext = nullptr;
     k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
-    ctx->launches += 3;
+    ctx->launches += 1;
   }
   ctx->launches += 4;
   CUDA_TRY(cudaGetLastError());

@@ -104,7 +104,7 @@ def test_lnlike_edge_semantics(oracle):
 
 
 def test_lnprob_pipeline_equals_fused_kernel():
-    """Large ensembles (>= 16384 walkers per call, 8192 with one component) run lnprob as a pipeline -- priors and parameters, the scheduled
+    """Large ensembles (>= 8192 walkers per call) run lnprob as a pipeline -- priors and parameters, the scheduled
     solve with the half-warp engine, fluxes -> chi^2; small ones as one fused launch (kernel=3 forces it).  Same
     arithmetic per model: identical -inf pattern, solve counts and values."""
     from radex_emcee_b200 import _lib
