@@ -1,19 +1,22 @@
 // lvg_small.cuh -- the cached engine of lvg_v2.cuh as kernels of its own, one instantiation per lead-block size:
 // one HALF-WARP per model for lead blocks of 12/16 levels, one warp per model for 20/24/28.
 //
-// In the forward sweep three quarters of the models keep every optically thick line below level 16, so
-// their cached iterations (lvg_v2.cuh: CACHED) eliminate a lead block of n = 12 or 16 levels with one row
-// per lane -- half of the warp idles, and the slab that has to stay on chip for them is 8.8 KB, not 19 KB.
-// This kernel runs those models two per warp (lanes 0-15 / 16-31, each half with its own slab and its own
-// iteration state), 26 (16 lead levels) or 32 (12 lead levels) models per SM instead of 12; one instantiation and
-// one launch per lead size, so the pivot loops are straight-line code with constant addresses.  It contains NO full elimination: launch B captures the
-// frozen top of such a model and parks lead block, response matrix and line bases (EXT_STRIDE doubles);
-// a model whose frozen lines turn thick is parked again and finished by launch C (v2::solve, sched = 4).
+// 93 % of the matrix() calls of the forward sweep are cached iterations (lvg_v2.cuh: CACHED): a lead block of
+// n = 4 KP levels eliminated one row per lane, the frozen levels through the response matrix.  Inside
+// k_lvg_solve_v2 they pay for the full engine they do not use (an 18.8 KB slab, 168 registers: 12 warps per SM), and
+// for n <= 16 -- three quarters of the sweep, nearly all of a converged ensemble -- half of the warp idles.  Here
+// every lead size has its own instantiation and launch: the pivot loops are straight-line code with constant
+// addresses, the slab holds just lead block + response matrix + pivot buffers + per-model line state (6.8 .. 15 KB),
+// and for n <= 16 two models share a warp (lanes 0-15 / 16-31, each half with its own slab, iteration state and
+// queue ticket): 32 / 26 / 16 / 16 / 15 models per SM for 12 / 16 / 20 / 24 / 28 lead levels.
+// There is NO full elimination in these kernels: launch A (v2::solve, sched = 1) captures the frozen top of a model
+// and parks lead block, response matrix and line bases (EXT_STRIDE doubles); a model whose frozen lines turn thick is
+// parked again and finished by launch C (v2::solve, sched = 4).
 //
-// Per model the arithmetic is the one of v2::lead_solve and of the iteration loop of v2::solve, operation
-// for operation and in the same association (the 32-lane butterflies are reproduced as "pair, then 16-lane
-// butterfly"), so the results are bit-identical to the single-launch path
-// (tests/test_gpu_solve.py::test_two_launch_schedule_is_bit_identical).
+// Per model the arithmetic is the one of v2::lead_solve and of the iteration loop of v2::solve, operation for
+// operation and in the same association (in a half-warp the 32-lane butterflies are reproduced as "pair, then
+// 16-lane butterfly"), so the results are bit-identical to the single-launch path
+// (tests/test_gpu_solve.py::test_two_launch_schedule_is_bit_identical, ::test_ordered_launches_...).
 //
 // What it replaces: the calls 2.. of matrix() + lubksb (emcee/pyradex/radex/radex.so@0x17f70, 0x17cb0) made
 // by run_radex's loop (emcee/pyradex/core.py:856-925) for these models.
@@ -36,7 +39,7 @@ using v2::NL;
 using v2::ld2;
 using v2::st2;
 
-using v2::KP_SMALL_MAX;               // lead blocks of 12 and 16 levels
+using v2::KP_SMALL_MAX;               // largest lead block (in panels) with an engine here
 using v2::EXT_LEAD;
 using v2::EXT_STRIDE;
 // ---- per-model shared-memory slab (doubles), for a lead block of N = 4 KP levels -------------------------
