@@ -8,7 +8,7 @@
 // every lead size has its own instantiation and launch: the pivot loops are straight-line code with constant
 // addresses, the slab holds just lead block + response matrix + pivot buffers + per-model line state (6.8 .. 15 KB),
 // and for n <= 16 two models share a warp (lanes 0-15 / 16-31, each half with its own slab, iteration state and
-// queue ticket): 32 / 26 / 16 / 16 / 15 models per SM for 12 / 16 / 20 / 24 / 28 lead levels.
+// queue ticket): 32 / 26 / 20 / 17 / 15 models per SM for 12 / 16 / 20 / 24 / 28 lead levels.
 // There is NO full elimination in these kernels: launch A (v2::solve, sched = 1) captures the frozen top of a model
 // and parks lead block, response matrix and line bases (EXT_STRIDE doubles); a model whose frozen lines turn thick is
 // parked again and finished by launch C (v2::solve, sched = 4).
@@ -23,10 +23,10 @@
 #pragma once
 
 #ifndef V2S_WARPS5
-#define V2S_WARPS5 16
+#define V2S_WARPS5 20
 #endif
 #ifndef V2S_WARPS6
-#define V2S_WARPS6 16
+#define V2S_WARPS6 17
 #endif
 #ifndef V2S_WARPS7
 #define V2S_WARPS7 15
