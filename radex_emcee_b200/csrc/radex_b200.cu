@@ -1718,7 +1718,9 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
 
 // Host-pointer entry.  Batches of more than 2 RB_HOST_CHUNK models are solved chunk by chunk, the results of one
 // chunk travelling to the host (copy stream) while the next one is being solved.
+#ifndef RB_HOST_CHUNK
 #define RB_HOST_CHUNK (1LL << 18)
+#endif
 
 int rb_solve_batch(rb_ctx *ctx, int64_t n, const double *tkin, const double *dens, const double *cdmol,
                    double deltav_kms, double tbg, int geometry, const rb_opts *opts, double *xpop, double *tex,
