@@ -59,6 +59,11 @@ typedef struct rb_opts {
   double abs_tol;      /* 1e-16 (core.py:857)                                             */
   double fk_epi;       /* h c / k_B used by the brightness epilogue (astropy, core.py:981-984) */
   double thc_epi;      /* 2 h c     used by the brightness epilogue                        */
+  int32_t park_max;    /* 0 = automatic.  3..7: largest lead block (in panels of 4 levels) that gets a cached-engine
+                          launch of its own in a scheduled batch (tests force 7 on small batches)            */
+  int32_t reserved;
+  int64_t lnprob_pipe_min; /* 0 = automatic (8192).  walkers per call from which lnprob runs as
+                          expand -> scheduled solve -> combine instead of one fused launch          */
 } rb_opts;
 
 /* observed SLED of one source (er1:229-240 get_source): up to RB_MAX_OBS CO lines */
@@ -126,6 +131,25 @@ int rb_lnprob2(rb_ctx *ctx, int64_t n, const double *P, const rb_obs *obs, const
 int rb_lnprob2_dev(rb_ctx *ctx, int64_t n, const double *P, const rb_obs *obs, const double *bounds,
                    int has_td, double t_d, double tbg, const rb_opts *opts, double *lnp, int64_t *nsolves_dev);
 
+/* ---- multi-source lnprob (BASELINE.json configs[3]: all flux.dat sources fitted concurrently; the reference
+ * loops over the sources one after the other, er1:389).  A source set is a device-resident table of
+ * (observed SLED, bounds, tbg, T_d) rows; src_id[n] (DEVICE int32, NULL = every walker belongs to source 0)
+ * names the row of each walker.  Same arithmetic per walker as rb_lnprob1/2.  More than one source always
+ * runs as one fused launch (the background temperature is a per-model quantity there).              */
+typedef struct rb_source {
+  rb_obs obs;
+  double bounds[16];   /* (4 ncomp) x 2 : lo, hi                                  */
+  double tbg;          /* 2.7315 (1 + z), er1:419                                  */
+  int32_t has_td;      /* two components: Gaussian prior on T_cold (er2:213-224)   */
+  int32_t reserved;
+  double t_d;
+} rb_source;
+typedef struct rb_srcset rb_srcset;
+int rb_srcset_create(rb_ctx *ctx, int32_t ncomp, int32_t nsrc, const rb_source *src, rb_srcset **out);
+void rb_srcset_destroy(rb_srcset *set);
+int rb_lnprob_src_dev(rb_ctx *ctx, const rb_srcset *set, int64_t n, const double *P, const int32_t *src_id,
+                      const rb_opts *opts, double *lnp, int64_t *nsolves_dev);
+
 /* ---- stretch move: replaces emcee.StretchMove.get_proposal + the accept loop of
  * emcee's RedBlueMove (un-vendored; call sites er1:483-499, er2:557-574).
  * All pointers are DEVICE pointers; asynchronous on the ctx stream.
@@ -142,6 +166,53 @@ int rb_stretch_propose_dev(rb_ctx *ctx, int64_t ns, int32_t ndim, const double *
 int rb_stretch_accept_dev(rb_ctx *ctx, int64_t ns, int32_t ndim, double *S, double *lnp_old, const double *Q,
                           const double *lnp_new, const double *logfac, uint64_t seed, uint64_t step,
                           int32_t half, int64_t gid0, int64_t gid_stride, int64_t *naccept);
+
+/* ---- stretch move, second form: the whole local ensemble X[nlocal, ndim] stays in place and the red/blue split
+ * is a function of (seed, step, global walker id), so that emcee's default randomize_split=True
+ * (RedBlueMove) is reproduced without communication and independently of the rank count.
+ *   ensemble  : N = nwalkers walkers, global ids 0..N-1; nsrc = N / walkers_per_source independent
+ *               sub-ensembles (one per fitted source) of W walkers each; a walker's partner comes from the
+ *               complementary half of its own sub-ensemble.
+ *   split     : blocks of `block` consecutive walkers (block | W, block even); in block b slot t of half h is
+ *               walker b*block + pi(h*block/2 + t), pi a keyed bijection of [0, block) drawn per (seed, step, b)
+ *               (randomize = 1), or 2t + h (randomize = 0: the parity split of the first form).
+ *   a rank    : owns the contiguous ids [gid_base, gid_base + nlocal), block | nlocal.
+ *   pack      : Chalf[nlocal/2, ndim] = positions of this rank's walkers of half `half`, in slot order; the
+ *               all-gather of these over the ranks (rank order) is `Call` = the half in global slot order.
+ *   propose2  : for every local slot of half `half`: walker s, partner c_j drawn from the W/2 slots of its
+ *               source in Call (the complementary half), q = c_j - (c_j - s) z, logfac; src_id[k] = source.
+ *   accept2   : accept test per slot; X, lnp updated in place; naccept[nlocal] per walker (emcee's
+ *               acceptance_fraction is per walker); *nan_count += NaN log-probabilities seen (emcee raises).
+ * RNG: Philox4x32-10 keyed by (seed, step, half, global walker id) exactly as in the first form.              */
+typedef struct rb_split {
+  int64_t nwalkers;
+  int64_t walkers_per_source;
+  int64_t block;
+  int32_t randomize;
+  int32_t reserved;
+  uint64_t seed;
+} rb_split;
+int rb_stretch_pack_dev(rb_ctx *ctx, const rb_split *split, uint64_t step, int32_t half, int64_t gid_base,
+                        int64_t nlocal, int32_t ndim, const double *X, double *Chalf);
+int rb_stretch_propose2_dev(rb_ctx *ctx, const rb_split *split, uint64_t step, int32_t half, int64_t gid_base,
+                            int64_t nlocal, int32_t ndim, const double *X, const double *Call, double a, double *Q,
+                            double *logfac, int32_t *src_id);
+int rb_stretch_accept2_dev(rb_ctx *ctx, const rb_split *split, uint64_t step, int32_t half, int64_t gid_base,
+                           int64_t nlocal, int32_t ndim, double *X, double *lnp, const double *Q, const double *lnp_new,
+                           const double *logfac, int64_t *naccept, int64_t *nan_count);
+
+/* ---- the sampler loop itself, device-resident: replaces EnsembleSampler.run_mcmc (call sites er1:490-499,
+ * er2:563-574) for one GPU -- nsteps stretch-move steps (two half-steps each: pack, propose2, lnprob of the
+ * source set, accept2) without returning to the host; ensembles whose half fits one fused lnprob launch are
+ * replayed from a CUDA graph of one step.  All pointers are DEVICE pointers.
+ *   X[N, ndim], lnp[N] : state, in/out (lnp must hold lnprob(X) on entry: rb_lnprob_src_dev)
+ *   naccept[N]         : += accepted proposals per walker        counters[2]: += NaN count, += solves
+ *   chain, lnp_chain   : NULL, or [nsteps / thin][N, ndim] and [nsteps / thin][N]: state after every thin-th step
+ * Multi-GPU runs call pack / all-gather (NCCL) / propose2 / rb_lnprob_src_dev / accept2 per half-step from one
+ * process per GPU (radex_emcee_b200/sampler.py; INTEGRATION.md shows the C++ form).                           */
+int rb_stretch_run_dev(rb_ctx *ctx, const rb_srcset *set, const rb_split *split, double a, uint64_t step0,
+                       int64_t nsteps, const rb_opts *opts, double *X, double *lnp, int64_t *naccept,
+                       int64_t *counters, int32_t thin, double *chain, double *lnp_chain);
 
 /* counters of the last solve/lnprob call on this ctx (device-measured, read back on request):
  * total matrix iterations summed over models, and kernels launched since ctx creation.        */

@@ -22,12 +22,23 @@ class RadexB200Error(RuntimeError):
 
 class rb_opts(C.Structure):
     _fields_ = [("stop_rule", C.c_int32), ("miniter", C.c_int32), ("maxiter", C.c_int32), ("kernel", C.c_int32),
-                ("abs_tol", C.c_double), ("fk_epi", C.c_double), ("thc_epi", C.c_double)]
+                ("abs_tol", C.c_double), ("fk_epi", C.c_double), ("thc_epi", C.c_double),
+                ("park_max", C.c_int32), ("reserved", C.c_int32), ("lnprob_pipe_min", C.c_int64)]
 
 
 class rb_obs(C.Structure):
     _fields_ = [("nobs", C.c_int32), ("jup", C.c_int32 * RB_MAX_OBS), ("flux", C.c_double * RB_MAX_OBS),
                 ("eflux", C.c_double * RB_MAX_OBS)]
+
+
+class rb_source(C.Structure):
+    _fields_ = [("obs", rb_obs), ("bounds", C.c_double * 16), ("tbg", C.c_double), ("has_td", C.c_int32),
+                ("reserved", C.c_int32), ("t_d", C.c_double)]
+
+
+class rb_split(C.Structure):
+    _fields_ = [("nwalkers", C.c_int64), ("walkers_per_source", C.c_int64), ("block", C.c_int64),
+                ("randomize", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -65,6 +76,17 @@ SIGNATURES = {
                                          C.c_uint64, C.c_int32, C.c_int64, C.c_int64, _vp, _vp]),
     "rb_stretch_accept_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64,
                                         C.c_int32, C.c_int64, C.c_int64, _vp]),
+    "rb_srcset_create": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(rb_source), C.POINTER(_vp)]),
+    "rb_srcset_destroy": (None, [_vp]),
+    "rb_lnprob_src_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.POINTER(rb_opts), _vp, _vp]),
+    "rb_stretch_pack_dev": (C.c_int, [_vp, C.POINTER(rb_split), C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_int32,
+                                      _vp, _vp]),
+    "rb_stretch_propose2_dev": (C.c_int, [_vp, C.POINTER(rb_split), C.c_uint64, C.c_int32, C.c_int64, C.c_int64,
+                                          C.c_int32, _vp, _vp, C.c_double, _vp, _vp, _vp]),
+    "rb_stretch_accept2_dev": (C.c_int, [_vp, C.POINTER(rb_split), C.c_uint64, C.c_int32, C.c_int64, C.c_int64,
+                                         C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rb_stretch_run_dev": (C.c_int, [_vp, _vp, C.POINTER(rb_split), C.c_double, C.c_uint64, C.c_int64,
+                                     C.POINTER(rb_opts), _vp, _vp, _vp, _vp, C.c_int32, _vp, _vp]),
     "rb_ctx_counters": (C.c_int, [_vp, _lp, _lp]),
     "rb_ctx_cache_stats": (C.c_int, [_vp, _lp]),
     "rb_fp64_peak": (C.c_int, [_vp, _dp]),
@@ -98,8 +120,6 @@ def check(rc):
 def default_opts(**kw) -> rb_opts:
     o = rb_opts()
     load().rb_default_opts(C.byref(o))
-    if "RB_KERNEL" in os.environ:       # debugging aid: force a kernel variant (see rb_opts.kernel)
-        o.kernel = int(os.environ["RB_KERNEL"])
     for k, v in kw.items():
         if v is not None:
             setattr(o, k, v)
@@ -121,6 +141,40 @@ def make_obs(jup, flux, eflux) -> rb_obs:
         o.flux[i] = float(flux[i])
         o.eflux[i] = float(eflux[i])
     return o
+
+
+def make_source(ncomp, jup, flux, eflux, bounds, tbg, T_d=None) -> rb_source:
+    b = np.ascontiguousarray(bounds, dtype=np.float64)
+    if b.shape != (4 * ncomp, 2):
+        raise ValueError("bounds must have shape (%d, 2)" % (4 * ncomp))
+    s = rb_source()
+    s.obs = make_obs(jup, flux, eflux)
+    for i, v in enumerate(b.ravel()):
+        s.bounds[i] = float(v)
+    s.tbg = float(tbg)
+    s.has_td = int(T_d is not None)
+    s.t_d = float(T_d) if T_d is not None else 0.0
+    return s
+
+
+class SourceSet:
+    """Device-resident table of fitted sources (rb_srcset): one row per source, same ncomp."""
+
+    def __init__(self, ctx: "Context", ncomp: int, sources):
+        L = load()
+        self.ctx, self.ncomp, self.nsrc = ctx, int(ncomp), len(sources)
+        arr = (rb_source * self.nsrc)(*sources)
+        h = _vp()
+        check(L.rb_srcset_create(ctx.handle, self.ncomp, self.nsrc, arr, C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle:
+                load().rb_srcset_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 def ptr(a):

@@ -6,8 +6,9 @@
 //   emcee/pyradex/radex/radex.so  readdata@0x1cf90 backrad@0x1be30 matrix@0x17f70 escprob@0xa9c0
 //                                 lubksb@0x17cb0 -> sgeir@0x16d50 -> sgefa@0xf3d0 / sgesl@0xdb70
 //
-// One warp owns one model (walker component) from parameter load to line fluxes; nothing but the
-// walker parameters and the requested outputs ever touches HBM.  See DESIGN.md for the layout.
+// One warp (or half-warp) owns one model (walker component).  Small batches run as ONE launch in which nothing but
+// the walker parameters and the requested outputs touches HBM; batches >= RB_SCHED_MIN run as ordered launches that
+// park each model's state (and the capture of its frozen top) in HBM between them.  See DESIGN.md for the layout.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -51,6 +52,7 @@ struct MolDev {
   const int *lev_ptr;                     // [nlev+1] CSR: lines incident on each level, in line order
   const int *lev_line;                    // [2*nline] line index, bit 30 set when the level is the upper one
   int part_id[RB_MAXPART], ntemp[RB_MAXPART], ncoll[RB_MAXPART];
+  double ln_frac[RB_MAXPART];             // lnprob: share of the walker's n(H2) that partner p receives (0 = no usable partner)
   const double *temps[RB_MAXPART];        // [ntemp]
   const int *lcu[RB_MAXPART], *lcl[RB_MAXPART];  // [ncoll] 0-based
   const double *rates_tc[RB_MAXPART];     // [ntemp][ncoll]
@@ -64,7 +66,9 @@ struct SolveCfg {
   int cache;                    // v2: frozen-top caching enabled (rb_opts.kernel != 2)
   int sched;                    // v2: launch scheduling allowed (rb_opts.kernel == 0 or 4)
   int small;                    // v2: cached engines as kernels of their own (lvg_small.cuh; kernel == 0)
-  int park_max;                 // v2: largest lead block (in panels) handed to them: 4 (half-warp engines only) or 7
+  int park_max;                 // v2: largest lead block (in panels) handed to them: 4 (half-warp engines only) or 7;
+                                //     0 = chosen from the batch size (rb_opts.park_max)
+  long long lnprob_pipe_min;    // walkers per call from which lnprob runs as a pipeline (rb_opts.lnprob_pipe_min)
   unsigned long long *stats;    // v2: [0] cached iterations, [1] captures, [2] invalidations
 };
 
@@ -90,6 +94,14 @@ struct rb_ctx {
   std::vector<cudaEvent_t> chunk_done;
   void *ln_buf = nullptr;                 // lnprob pipeline: model parameters, observed-line brightness, status (grow-only)
   size_t ln_bytes = 0;
+  rb_source *src_one = nullptr;           // device copy of the source of the last rb_lnprob1/2 call ...
+  rb_source src_one_host{};               // ... and what it holds (no transfer while the caller keeps passing the same source)
+  bool src_one_valid = false;
+  bool ln_partners_ok = false;            // lnprob: the file has H2, or p-H2 / o-H2, as a collision partner
+  void *samp_buf = nullptr;               // rb_stretch_run_dev: complementary half, proposals, their lnprob, step counter (grow-only)
+  size_t samp_bytes = 0;
+  cudaGraphExec_t samp_graph = nullptr;   // one stretch-move step, captured for the arguments in samp_key
+  std::vector<unsigned char> samp_key;
   long long launches = 0;
   long long last_total_iters = 0;
 };
@@ -319,7 +331,7 @@ __device__ void v1_lu_solve(const WarpMem &w, int nl, int lane) {
 // One full solve.  On return w.xpop/tex/taul/backi hold the state pyradex would read back.
 // Returns the pyradex iteration counter; *status gets the rb_model_status bits.
 __device__ int v1_solve(const MolDev &mol, const WarpMem &w, int lane, double tkin, const double *dens, double cdmol,
-                        const SolveCfg &cfg, int *status) {
+                        const double tbg, const SolveCfg &cfg, int *status) {
   const int nl = mol.nlev, nn = mol.nline;
   int st = 0;
   if (!(tkin > 0.0 && tkin <= 1.0e4)) st |= RB_ST_T_RANGE;
@@ -338,7 +350,7 @@ __device__ int v1_solve(const MolDev &mol, const WarpMem &w, int lane, double tk
   // background (backrad, tbg > 0 branch, radex.so@0x1be30): backi = totalb, trj = tbg
   for (int l = lane; l < nn; l += 32) {
     const double xnu = mol.xnu[l];
-    const double hnu = RB_FK * xnu / cfg.tbg;
+    const double hnu = RB_FK * xnu / tbg;
     w.backi[l] = (hnu >= 160.0) ? 1.0e-30 : RB_THC * (xnu * xnu * xnu) / (exp(hnu) - 1.0);
     w.tex[l] = 0.0;
     w.taul[l] = 0.0;
@@ -362,7 +374,7 @@ __device__ int v1_solve(const MolDev &mol, const WarpMem &w, int lane, double tk
       const double xnu = mol.xnu[l];
       double beta, exr;
       if (it == 0) {
-        const double etr = RB_FK * xnu / cfg.tbg;
+        const double etr = RB_FK * xnu / tbg;
         exr = (etr >= 160.0) ? 0.0 : 1.0 / (exp(etr) - 1.0);
         beta = 1.0;
       } else {
@@ -513,7 +525,7 @@ __global__ void __launch_bounds__(256) k_lvg_solve_v1(MolDev mol, SolveCfg cfg, 
     double dens[RB_MAXPART];
     for (int p = 0; p < mol.npart; ++p) dens[p] = io.dens[idx * mol.npart + p];
     int st = 0;
-    const int it = v1_solve(mol, w, lane, io.tkin[idx], dens, io.cdmol[idx], cfg, &st);
+    const int it = v1_solve(mol, w, lane, io.tkin[idx], dens, io.cdmol[idx], cfg.tbg, cfg, &st);
     const bool bad = (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) != 0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     int nonfinite = 0;
@@ -546,12 +558,10 @@ __global__ void __launch_bounds__(256) k_lvg_solve_v1(MolDev mol, SolveCfg cfg, 
 // ------------------------------------------------------------------------------------------------
 struct LnprobIO {
   long long n;
-  const double *P;       // n x (4*NCOMP)
-  double *lnp;           // n
-  rb_obs obs;
-  double bounds[16];     // (4*NCOMP) x 2
-  int has_td;
-  double t_d;
+  const double *P;        // n x (4*NCOMP)
+  double *lnp;            // n
+  const rb_source *srcs;  // device table: observed SLED, bounds, tbg, T_d per fitted source
+  const int *src_id;      // n: row of each walker, or nullptr = row 0
   unsigned long long *counters;
 };
 
@@ -589,6 +599,38 @@ __device__ double lnprior2(const double *p, const double *b, int has_td, double 
   return logp;
 }
 
+// lnlike (emcee_radex.py:132-167 / emcee_radex_2comp.py:169-196) by one warp: lane i < nobs holds the model flux of
+// observed line i.  Returns lp + ll, or -inf wherever the reference does.
+__device__ __forceinline__ double lnlike_warp(const rb_source &S, const double model, const double lp, const int lane) {
+  int bad = 0;
+  double r2 = 0.0, le = 0.0;
+  if (lane < S.obs.nobs) {
+    const double f = S.obs.flux[lane];
+    const double e = fmax(fabs(S.obs.eflux[lane]), 1.0e-12);
+    if (!isfinite(f) || !isfinite(model) || !isfinite(e)) {
+      bad = 1;
+    } else {
+      const double r = (f - model) / e;
+      const double max_safe = 1.3407807929942596e+153;  // sqrt(DBL_MAX)/10
+      if (!isfinite(r) || fabs(r) > max_safe) bad = 1;
+      r2 = r * r;
+      le = log(e);
+    }
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  const double chi2 = warp_sum(r2), logterm = 2.0 * warp_sum(le);
+  if (bad) return neg_inf();
+  const double ll = -0.5 * (chi2 + logterm);
+  return isfinite(ll) ? lp + ll : neg_inf();
+}
+
+// collider densities of one walker component: total n(H2) split as the drivers do (opr = 3, emcee_radex.py:95-96)
+// through the per-partner fractions worked out on the host (MolDev::ln_frac, see lnprob_partner_fractions)
+__device__ __forceinline__ void lnprob_dens(const MolDev &mol, const double dens_tot, double *dens) {
+#pragma unroll
+  for (int q = 0; q < RB_MAXPART; ++q) dens[q] = (q < mol.npart) ? mol.ln_frac[q] * dens_tot : 0.0;
+}
+
 template <int NCOMP>
 __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, LnprobIO io) {
   extern __shared__ double smem[];
@@ -596,17 +638,17 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
   const int nl = mol.nlev, nn = mol.nline;
   const WarpMem w = carve(smem + (size_t)wib * v1_warp_doubles(nl, nn), nl, nn);
   constexpr int ND = 4 * NCOMP;
-  const double fortho = 3.0 / (1.0 + 3.0);  // opr = 3 (emcee_radex.py:95-96)
   unsigned long long iters = 0, solves = 0;
   for (;;) {
     unsigned long long idx = 0;
     if (lane == 0) idx = atomicAdd(&io.counters[0], 1ULL);
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if ((long long)idx >= io.n) break;
+    const rb_source &S = io.srcs[io.src_id ? io.src_id[idx] : 0];
     double p[ND];
 #pragma unroll
     for (int i = 0; i < ND; ++i) p[i] = io.P[idx * ND + i];
-    const double lp = (NCOMP == 1) ? lnprior1(p, io.bounds) : lnprior2(p, io.bounds, io.has_td, io.t_d);
+    const double lp = (NCOMP == 1) ? lnprior1(p, S.bounds) : lnprior2(p, S.bounds, S.has_td, S.t_d);
     double result = neg_inf();
     if (isfinite(lp)) {  // prior short-circuit: no solve (emcee_radex.py:178-180)
       double model = 0.0;  // lane i < nobs holds the model flux of observed line i
@@ -614,48 +656,23 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
 #pragma unroll
       for (int c = 0; c < NCOMP; ++c) {
         if (value_error) break;
-        const double dens_tot = pow(10.0, p[4 * c + 0]);
         double dens[RB_MAXPART];
-        for (int q = 0; q < mol.npart; ++q)
-          dens[q] = (mol.part_id[q] == 2) ? (1.0 - fortho) * dens_tot : (mol.part_id[q] == 3) ? fortho * dens_tot : 0.0;
+        lnprob_dens(mol, pow(10.0, p[4 * c + 0]), dens);
         int st = 0;
-        const int it = v1_solve(mol, w, lane, pow(10.0, p[4 * c + 1]), dens, pow(10.0, p[4 * c + 2]), cfg, &st);
+        const int it = v1_solve(mol, w, lane, pow(10.0, p[4 * c + 1]), dens, pow(10.0, p[4 * c + 2]), S.tbg, cfg, &st);
         if (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) {
           value_error = true;  // ValueError -> -inf (emcee_radex.py:134-137)
         } else {
           ++solves;
           iters += (unsigned long long)((st & RB_ST_MAXITER) ? it : it + 1);
-          if (lane < io.obs.nobs) {
-            const double s = rb_surf(mol, w, io.obs.jup[lane] - 1, cfg);
-            model += s * pow(10.0, p[4 * c + 3]) * 1.0e23;  // x size [sr] x 1 km/s -> Jy km/s
+          if (lane < S.obs.nobs) {
+            const double sf = rb_surf(mol, w, S.obs.jup[lane] - 1, cfg);
+            model += sf * pow(10.0, p[4 * c + 3]) * 1.0e23;  // x size [sr] x 1 km/s -> Jy km/s
           }
         }
         __syncwarp();
       }
-      if (!value_error) {
-        // lnlike (emcee_radex.py:132-167 / emcee_radex_2comp.py:169-196)
-        int bad = 0;
-        double r2 = 0.0, le = 0.0;
-        if (lane < io.obs.nobs) {
-          const double f = io.obs.flux[lane];
-          const double e = fmax(fabs(io.obs.eflux[lane]), 1.0e-12);
-          if (!isfinite(f) || !isfinite(model) || !isfinite(e)) {
-            bad = 1;
-          } else {
-            const double r = (f - model) / e;
-            const double max_safe = 1.3407807929942596e+153;  // sqrt(DBL_MAX)/10
-            if (!isfinite(r) || fabs(r) > max_safe) bad = 1;
-            r2 = r * r;
-            le = log(e);
-          }
-        }
-        bad = __any_sync(0xffffffffu, bad);
-        const double chi2 = warp_sum(r2), logterm = 2.0 * warp_sum(le);
-        if (!bad) {
-          const double ll = -0.5 * (chi2 + logterm);
-          result = isfinite(ll) ? lp + ll : neg_inf();
-        }
-      }
+      if (!value_error) result = lnlike_warp(S, model, lp, lane);
     }
     if (lane == 0) io.lnp[idx] = result;
   }
@@ -673,7 +690,7 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
 // walkers per call from which lnprob runs as a pipeline.  Measured (walker-steps/s, pipeline vs fused launch, with launch B
 // and the engine launches overlapping): 1 component, 8192 walkers per call 4.35e6 vs 3.64e6; 2 components, 8192 per call
 // 1.86e6 vs 1.66e6, 16384 per call 2.49e6 vs 1.80e6
-#define RB_LNPROB_PIPE_MIN(ncomp) 8192
+#define RB_LNPROB_PIPE_MIN 8192
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, SolveCfg cfg, SolveIO io) {
   extern __shared__ double smem[];
@@ -697,7 +714,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
     for (int p = 0; p < RB_MAXPART; ++p) dens[p] = (p < mol.npart) ? io.dens[idx * mol.npart + p] : 0.0;
     int st = 0, key = -1;
     const double cdmol = io.cdmol[idx];
-    const int it = v2::solve(mol, sm, gB, phase, lane, io.tkin[idx], dens, cdmol, cfg, &st, io.sched,
+    const int it = v2::solve(mol, sm, gB, phase, lane, io.tkin[idx], dens, cdmol, cfg.tbg, cfg, &st, io.sched,
                              io.state ? io.state + idx * v2::STATE_STRIDE : nullptr, &key,
                              (io.sched == 1 && io.ext) ? io.ext + idx * v2::EXT_STRIDE : nullptr);
     if (io.sched == 1 && lane == 0) io.keys[idx] = (st & v2::ST_PARKED) ? key : -1;
@@ -711,14 +728,14 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
     int nonfinite = 0;
     if (io.obs_surf && lane < io.nobs) {
       double tex, tau, sf = qnan;
-      if (!bad) v2::line_results(mol, sm, io.obs_line[lane], cdmol, cfg, tex, tau, sf);
+      if (!bad) v2::line_results(mol, sm, io.obs_line[lane], cdmol, cfg.tbg, cfg, tex, tau, sf);
       io.obs_surf[idx * RB_MAX_OBS + lane] = sf;
     }
 #pragma unroll 1
     for (int l = io.obs_surf ? nn : lane; l < nn; l += 32) {
       double tex = qnan, tau = qnan, sf = qnan;
       if (!bad) {
-        v2::line_results(mol, sm, l, cdmol, cfg, tex, tau, sf);
+        v2::line_results(mol, sm, l, cdmol, cfg.tbg, cfg, tex, tau, sf);
         if (!isfinite(sf)) nonfinite = 1;
       }
       if (io.surf) io.surf[idx * nn + l] = sf;
@@ -1045,70 +1062,45 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lnprob_v2(MolDev mol, Solv
   if (lane == 0) v2::mbar_init(sm + v2::O_MBAR, 1);
   __syncwarp();
   constexpr int ND = 4 * NCOMP;
-  const double fortho = 3.0 / (1.0 + 3.0);  // opr = 3 (emcee_radex.py:95-96)
   unsigned long long iters = 0, solves = 0;
   for (;;) {
     unsigned long long idx = 0;
     if (lane == 0) idx = atomicAdd(&io.counters[0], 1ULL);
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if ((long long)idx >= io.n) break;
+    const rb_source &S = io.srcs[io.src_id ? io.src_id[idx] : 0];
     double p[ND];
 #pragma unroll
     for (int i = 0; i < ND; ++i) p[i] = io.P[idx * ND + i];
-    const double lp = (NCOMP == 1) ? lnprior1(p, io.bounds) : lnprior2(p, io.bounds, io.has_td, io.t_d);
+    const double lp = (NCOMP == 1) ? lnprior1(p, S.bounds) : lnprior2(p, S.bounds, S.has_td, S.t_d);
     double result = neg_inf();
     if (isfinite(lp)) {  // prior short-circuit: no solve (emcee_radex.py:178-180)
       double model = 0.0;
       bool value_error = false;
+      const double tbg = S.tbg;
 #pragma unroll
       for (int c = 0; c < NCOMP; ++c) {
         if (value_error) break;
-        const double dens_tot = pow(10.0, p[4 * c + 0]);
         double dens[RB_MAXPART];
-#pragma unroll
-        for (int q = 0; q < RB_MAXPART; ++q)
-          dens[q] = (q < mol.npart && mol.part_id[q] == 2) ? (1.0 - fortho) * dens_tot
-                    : (q < mol.npart && mol.part_id[q] == 3) ? fortho * dens_tot : 0.0;
+        lnprob_dens(mol, pow(10.0, p[4 * c + 0]), dens);
         int st = 0;
         const double cdmol = pow(10.0, p[4 * c + 2]);
-        const int it = v2::solve(mol, sm, gB, phase, lane, pow(10.0, p[4 * c + 1]), dens, cdmol, cfg, &st);
+        const int it = v2::solve(mol, sm, gB, phase, lane, pow(10.0, p[4 * c + 1]), dens, cdmol, tbg, cfg, &st);
         if (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) {
           value_error = true;  // ValueError -> -inf (emcee_radex.py:134-137)
         } else {
           ++solves;
           iters += (unsigned long long)((st & RB_ST_MAXITER) ? it : it + 1);
           // only the observed lines' fluxes are needed: lane i < nobs evaluates line Jup_i - 1
-          if (lane < io.obs.nobs) {
+          if (lane < S.obs.nobs) {
             double tex, tau, sf;
-            v2::line_results(mol, sm, io.obs.jup[lane] - 1, cdmol, cfg, tex, tau, sf);
+            v2::line_results(mol, sm, S.obs.jup[lane] - 1, cdmol, tbg, cfg, tex, tau, sf);
             model += sf * pow(10.0, p[4 * c + 3]) * 1.0e23;
           }
         }
         __syncwarp();
       }
-      if (!value_error) {
-        int bad = 0;
-        double r2 = 0.0, le = 0.0;
-        if (lane < io.obs.nobs) {
-          const double f = io.obs.flux[lane];
-          const double e = fmax(fabs(io.obs.eflux[lane]), 1.0e-12);
-          if (!isfinite(f) || !isfinite(model) || !isfinite(e)) {
-            bad = 1;
-          } else {
-            const double r = (f - model) / e;
-            const double max_safe = 1.3407807929942596e+153;  // sqrt(DBL_MAX)/10
-            if (!isfinite(r) || fabs(r) > max_safe) bad = 1;
-            r2 = r * r;
-            le = log(e);
-          }
-        }
-        bad = __any_sync(0xffffffffu, bad);
-        const double chi2 = warp_sum(r2), logterm = 2.0 * warp_sum(le);
-        if (!bad) {
-          const double ll = -0.5 * (chi2 + logterm);
-          result = isfinite(ll) ? lp + ll : neg_inf();
-        }
-      }
+      if (!value_error) result = lnlike_warp(S, model, lp, lane);
     }
     if (lane == 0) io.lnp[idx] = result;
   }
@@ -1135,18 +1127,16 @@ __global__ void k_lnprob_expand(MolDev mol, LnprobIO io, LnprobPipe pp) {
   double p[ND];
 #pragma unroll
   for (int i = 0; i < ND; ++i) p[i] = io.P[idx * ND + i];
-  const double lp = (NCOMP == 1) ? lnprior1(p, io.bounds) : lnprior2(p, io.bounds, io.has_td, io.t_d);
+  const rb_source &S = io.srcs[0];   // the pipeline serves one source per call
+  const double lp = (NCOMP == 1) ? lnprior1(p, S.bounds) : lnprior2(p, S.bounds, S.has_td, S.t_d);
   io.lnp[idx] = lp;   // the prior waits here for k_lnprob_combine
-  const double fortho = 3.0 / (1.0 + 3.0);
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
   for (int c = 0; c < NCOMP; ++c) {
     const long long m = idx * NCOMP + c;
     const bool go = isfinite(lp);   // prior short-circuit: a NaN temperature is refused before any work is done
     const double dens_tot = pow(10.0, p[4 * c + 0]);
-    for (int q = 0; q < mol.npart; ++q)
-      pp.dens[m * mol.npart + q] = (mol.part_id[q] == 2) ? (1.0 - fortho) * dens_tot
-                                   : (mol.part_id[q] == 3) ? fortho * dens_tot : 0.0;
+    for (int q = 0; q < mol.npart; ++q) pp.dens[m * mol.npart + q] = mol.ln_frac[q] * dens_tot;
     pp.tkin[m] = go ? pow(10.0, p[4 * c + 1]) : qnan;
     pp.cdmol[m] = pow(10.0, p[4 * c + 2]);
   }
@@ -1158,6 +1148,7 @@ __global__ void k_lnprob_combine(LnprobIO io, LnprobPipe pp) {
   const int lane = threadIdx.x & 31;
   const long long idx = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;   // one warp per walker
   if (idx >= io.n) return;
+  const rb_source &S = io.srcs[0];
   const double lp = io.lnp[idx];
   double result = neg_inf();
   unsigned long long solves = 0;
@@ -1171,32 +1162,10 @@ __global__ void k_lnprob_combine(LnprobIO io, LnprobPipe pp) {
         value_error = true;
       } else {
         ++solves;
-        if (lane < io.obs.nobs) model += pp.obs_surf[m * RB_MAX_OBS + lane] * pow(10.0, io.P[idx * ND + 4 * c + 3]) * 1.0e23;
+        if (lane < S.obs.nobs) model += pp.obs_surf[m * RB_MAX_OBS + lane] * pow(10.0, io.P[idx * ND + 4 * c + 3]) * 1.0e23;
       }
     }
-    if (!value_error) {
-      int bad = 0;
-      double r2 = 0.0, le = 0.0;
-      if (lane < io.obs.nobs) {
-        const double f = io.obs.flux[lane];
-        const double e = fmax(fabs(io.obs.eflux[lane]), 1.0e-12);
-        if (!isfinite(f) || !isfinite(model) || !isfinite(e)) {
-          bad = 1;
-        } else {
-          const double r = (f - model) / e;
-          const double max_safe = 1.3407807929942596e+153;  // sqrt(DBL_MAX)/10
-          if (!isfinite(r) || fabs(r) > max_safe) bad = 1;
-          r2 = r * r;
-          le = log(e);
-        }
-      }
-      bad = __any_sync(0xffffffffu, bad);
-      const double chi2 = warp_sum(r2), logterm = 2.0 * warp_sum(le);
-      if (!bad) {
-        const double ll = -0.5 * (chi2 + logterm);
-        result = isfinite(ll) ? lp + ll : neg_inf();
-      }
-    }
+    if (!value_error) result = lnlike_warp(S, model, lp, lane);
   }
   if (lane == 0) {
     io.lnp[idx] = result;
@@ -1272,6 +1241,8 @@ __global__ void k_stretch_accept(long long ns, int ndim, double *S, double *lnp_
 }
 
 
+#include "stretch.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // FP64 FMA peak probe: the roofline denominator for the solve kernels is the vector FP64 pipe,
 // which MEASURED_PEAKS.json does not cover, so bench.py measures it live with this kernel.
@@ -1323,7 +1294,8 @@ SolveCfg make_cfg(const rb_ctx *ctx, const rb_opts *o, double deltav_kms, double
   c.cache = (d.kernel != 2);
   c.sched = (d.kernel == 0 || d.kernel == 4);
   c.small = (d.kernel == 0);
-  c.park_max = 4;
+  c.park_max = (d.park_max >= v2::KP_CACHE_MIN && d.park_max <= v2::KP_SMALL_MAX) ? d.park_max : 0;
+  c.lnprob_pipe_min = (d.lnprob_pipe_min > 0) ? d.lnprob_pipe_min : RB_LNPROB_PIPE_MIN;
   c.stats = ctx->counters + 3;
   return c;
 }
@@ -1369,11 +1341,14 @@ bool use_v2(const rb_ctx *ctx, const rb_opts *o) {
   return kernel != 1 && kernel <= 4 && kernel >= 0 && ctx->mol.nlev == v2::NL && ctx->mol.nline <= v2::MAXLINE;
 }
 
+// One CTA per SM; a batch with fewer models than 12 warps x SMs spreads them over the SMs (a small ensemble's
+// half-step is 50 models: one warp each on 50 SMs, not 12 warps on each of 5)
 Launch v2_launch(rb_ctx *ctx, long long n) {
   Launch L;
-  L.warps_per_block = V2_WARPS;
-  L.smem = (size_t)V2_WARPS * v2::SLAB * sizeof(double);
-  const long long need = (n + V2_WARPS - 1) / V2_WARPS;
+  const long long per_sm = (n + ctx->sm_count - 1) / ctx->sm_count;
+  L.warps_per_block = (int)std::max<long long>(1, std::min<long long>(per_sm, V2_WARPS));
+  L.smem = (size_t)L.warps_per_block * v2::SLAB * sizeof(double);
+  const long long need = (n + L.warps_per_block - 1) / L.warps_per_block;
   L.blocks = (int)std::max<long long>(1, std::min<long long>(need, ctx->sm_count));
   return L;
 }
@@ -1405,6 +1380,9 @@ void rb_default_opts(rb_opts *o) {
   // astropy (CODATA 2018) h c / k_B and 2 h c in cgs, which is what core.py:981-984 evaluates to
   o->fk_epi = 1.4387768775039338;
   o->thc_epi = 3.9728917142978115e-16;
+  o->park_max = 0;
+  o->reserved = 0;
+  o->lnprob_pipe_min = 0;
 }
 
 int rb_device_count(void) {
@@ -1484,6 +1462,21 @@ int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
     UP(pt.rates_tc, m.rates_tc[p]);
   }
 #undef UP
+  {
+    // lnprob's collider densities (emcee_radex.py:122-124 sets {'oH2': fortho n, 'pH2': (1 - fortho) n}, opr = 3):
+    // pyradex folds them into H2 when the file lists that partner (core.py:551-556), else keeps them apart;
+    // every other partner gets zero density
+    const double fortho = 3.0 / (1.0 + 3.0);
+    bool has_h2 = false;
+    for (int p = 0; p < mol->npart; ++p) has_h2 |= (mol->partners[p].id == 1);
+    for (int p = 0; p < RB_MAXPART; ++p) m.ln_frac[p] = 0.0;
+    for (int p = 0; p < mol->npart; ++p) {
+      const int id = mol->partners[p].id;
+      if (has_h2) m.ln_frac[p] = (id == 1) ? 1.0 : 0.0;
+      else m.ln_frac[p] = (id == 2) ? 1.0 - fortho : (id == 3) ? fortho : 0.0;
+      if (m.ln_frac[p] > 0.0) ctx->ln_partners_ok = true;
+    }
+  }
   if (rc == RB_OK && cudaMalloc(&ctx->counters, 16 * sizeof(unsigned long long)) != cudaSuccess) {
     rb_set_error("cudaMalloc(counters) failed");
     rc = RB_ERR_CUDA;
@@ -1534,6 +1527,9 @@ void rb_ctx_destroy(rb_ctx *ctx) {
   if (ctx->sched_buf) cudaFree(ctx->sched_buf);
   if (ctx->sched_small) cudaFree(ctx->sched_small);
   if (ctx->ln_buf) cudaFree(ctx->ln_buf);
+  if (ctx->src_one) cudaFree(ctx->src_one);
+  if (ctx->samp_buf) cudaFree(ctx->samp_buf);
+  if (ctx->samp_graph) cudaGraphExecDestroy(ctx->samp_graph);
   for (cudaEvent_t ev : ctx->chunk_done) cudaEventDestroy(ev);
   for (int j = 0; j < 6; ++j) {
     if (ctx->side[j]) cudaStreamDestroy(ctx->side[j]);
@@ -1594,8 +1590,7 @@ static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg_in, SolveIO io
   }
   const long long n = io.n;
   SolveCfg cfg = cfg_in;
-  cfg.park_max = (n >= RB_MID_MIN) ? v2::KP_SMALL_MAX : 4;
-  if (const char *e = getenv("RB_PARK_MAX")) cfg.park_max = atoi(e);   // A/B aid
+  if (cfg.park_max == 0) cfg.park_max = (n >= RB_MID_MIN) ? v2::KP_SMALL_MAX : 4;
   const bool small = cfg.small != 0;   // the parked captures take 10.9 KB per model
   const size_t b_state = align256((size_t)n * v2::STATE_STRIDE * sizeof(double)), b_int = align256((size_t)n * sizeof(int));
   const size_t b_ext = small ? align256((size_t)n * v2::EXT_STRIDE * sizeof(double)) : 0;
@@ -1802,40 +1797,61 @@ int rb_solve_batch(rb_ctx *ctx, int64_t n, const double *tkin, const double *den
   return RB_OK;
 }
 
-static int lnprob_dev(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const rb_obs *obs, const double *bounds,
-                      int has_td, double t_d, double tbg, const rb_opts *opts, double *lnp) {
-  int rc = check_common(ctx, 1.0, tbg, RB_GEOM_LVG);
-  if (rc != RB_OK) return rc;
-  if (n < 0 || !obs || !bounds || (n > 0 && (!P || !lnp))) {
-    rb_set_error("rb_lnprob: null argument");
-    return RB_ERR_ARG;
-  }
-  if (obs->nobs < 1 || obs->nobs > RB_MAX_OBS) {
+struct rb_srcset {
+  rb_ctx *ctx = nullptr;
+  int ncomp = 1, nsrc = 0;
+  rb_source *d = nullptr;          // device table
+  std::vector<rb_source> h;        // host copy (argument checks; row 0 drives the single-source pipeline)
+};
+
+static int check_source(const rb_ctx *ctx, const rb_source &S) {
+  if (S.obs.nobs < 1 || S.obs.nobs > RB_MAX_OBS) {
     rb_set_error("rb_lnprob: nobs must be in 1..RB_MAX_OBS");
     return RB_ERR_ARG;
   }
-  for (int i = 0; i < obs->nobs; ++i)
-    if (obs->jup[i] < 1 || obs->jup[i] > ctx->mol.nline) {
+  for (int i = 0; i < S.obs.nobs; ++i)
+    if (S.obs.jup[i] < 1 || S.obs.jup[i] > ctx->mol.nline) {
       rb_set_error("rb_lnprob: Jup outside the molecule's line list");
       return RB_ERR_ARG;
     }
+  if (!(S.tbg > 0.0)) {
+    rb_set_error("deltav and tbg must be positive");
+    return RB_ERR_ARG;
+  }
+  return RB_OK;
+}
+
+// lnprob of n walkers against the device table d_srcs (row src_id[i], or row 0); h0 = host copy of row 0.
+static int lnprob_core(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const rb_source *d_srcs, int nsrc,
+                       const rb_source &h0, const int *src_id, const rb_opts *opts, double *lnp) {
+  if (!ctx) {
+    rb_set_error("null context");
+    return RB_ERR_ARG;
+  }
+  if (n < 0 || (n > 0 && (!P || !lnp))) {
+    rb_set_error("rb_lnprob: null argument");
+    return RB_ERR_ARG;
+  }
+  if (!ctx->ln_partners_ok) {
+    // the drivers set {'oH2', 'pH2'} (emcee_radex.py:122-124), which pyradex folds into H2 when the file has that
+    // partner (core.py:551-556); a file with neither has all-zero colliders there (ValueError)
+    rb_set_error("rb_lnprob: the molecular file has no H2 / p-H2 / o-H2 collision partner");
+    return RB_ERR_ARG;
+  }
   if (n == 0) return RB_OK;
   CUDA_TRY(cudaSetDevice(ctx->device));
-  const SolveCfg cfg = make_cfg(ctx, opts, 1.0, tbg, RB_GEOM_LVG);  // deltav=1 km/s, LVG (emcee_radex.py:108-117)
+  const SolveCfg cfg = make_cfg(ctx, opts, 1.0, h0.tbg, RB_GEOM_LVG);  // deltav=1 km/s, LVG (emcee_radex.py:108-117)
   CUDA_TRY(cudaMemsetAsync(ctx->counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
   LnprobIO io;
   memset(&io, 0, sizeof(io));
   io.n = n;
   io.P = P;
   io.lnp = lnp;
-  io.obs = *obs;
-  memcpy(io.bounds, bounds, sizeof(double) * 8 * ncomp);
-  io.has_td = has_td;
-  io.t_d = t_d;
+  io.srcs = d_srcs;
+  io.src_id = (nsrc > 1) ? src_id : nullptr;
   io.counters = ctx->counters;
-  long long pipe_min = RB_LNPROB_PIPE_MIN(ncomp);
-  if (const char *e = getenv("RB_LNPROB_PIPE_MIN")) pipe_min = atoll(e);   // A/B aid
-  if (use_v2(ctx, opts) && cfg.sched && cfg.small && cfg.cache && n >= pipe_min && n * ncomp >= RB_SCHED_MIN) {
+  if (nsrc == 1 && use_v2(ctx, opts) && cfg.sched && cfg.small && cfg.cache && n >= cfg.lnprob_pipe_min &&
+      n * ncomp >= RB_SCHED_MIN) {
     // large ensembles: expand -> scheduled solve of all n x ncomp models (half-warp engine) -> combine
     const long long m = n * ncomp;
     const int np = ctx->mol.npart;
@@ -1860,8 +1876,8 @@ static int lnprob_dev(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const 
     SolveIO sio{m, pp.tkin, pp.dens, pp.cdmol, nullptr, nullptr, nullptr, nullptr, nullptr, pp.status, ctx->counters,
                 0, nullptr, nullptr, nullptr, nullptr};
     sio.obs_surf = pp.obs_surf;
-    sio.nobs = obs->nobs;
-    for (int i = 0; i < obs->nobs; ++i) sio.obs_line[i] = obs->jup[i] - 1;
+    sio.nobs = h0.obs.nobs;
+    for (int i = 0; i < h0.obs.nobs; ++i) sio.obs_line[i] = h0.obs.jup[i] - 1;
     if (ncomp == 1)
       k_lnprob_expand<1><<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(ctx->mol, io, pp);
     else
@@ -1890,6 +1906,36 @@ static int lnprob_dev(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const 
   CUDA_TRY(cudaGetLastError());
   ctx->launches += 1;
   return RB_OK;
+}
+
+// rb_lnprob1/2: one source given by value.  Its device copy lives in the ctx and is refreshed only when the caller
+// passes a different source than last time (a sampler passes the same one every half-step: no transfer, no sync).
+static int lnprob_dev(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const rb_obs *obs, const double *bounds,
+                      int has_td, double t_d, double tbg, const rb_opts *opts, double *lnp) {
+  int rc = check_common(ctx, 1.0, tbg, RB_GEOM_LVG);
+  if (rc != RB_OK) return rc;
+  if (!obs || !bounds) {
+    rb_set_error("rb_lnprob: null argument");
+    return RB_ERR_ARG;
+  }
+  rb_source S;
+  memset(&S, 0, sizeof(S));
+  S.obs = *obs;
+  memcpy(S.bounds, bounds, sizeof(double) * 8 * ncomp);
+  S.tbg = tbg;
+  S.has_td = has_td;
+  S.t_d = t_d;
+  rc = check_source(ctx, S);
+  if (rc != RB_OK) return rc;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!ctx->src_one) CUDA_TRY(cudaMalloc(&ctx->src_one, sizeof(rb_source)));
+  if (!ctx->src_one_valid || memcmp(&S, &ctx->src_one_host, sizeof(S)) != 0) {
+    ctx->src_one_host = S;   // the copy reads the ctx's own (stable) host memory
+    ctx->src_one_valid = true;
+    CUDA_TRY(cudaMemcpyAsync(ctx->src_one, &ctx->src_one_host, sizeof(S), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  return lnprob_core(ctx, ncomp, n, P, ctx->src_one, 1, S, nullptr, opts, lnp);
 }
 
 static int lnprob_host(rb_ctx *ctx, int ncomp, int64_t n, const double *P, const rb_obs *obs, const double *bounds,
@@ -1987,6 +2033,288 @@ int rb_stretch_accept_dev(rb_ctx *ctx, int64_t ns, int32_t ndim, double *S, doub
                                                     reinterpret_cast<unsigned long long *>(naccept));
   CUDA_TRY(cudaGetLastError());
   ctx->launches += 1;
+  return RB_OK;
+}
+
+
+// ---- source sets, multi-source lnprob ---------------------------------------------------------------------------
+int rb_srcset_create(rb_ctx *ctx, int32_t ncomp, int32_t nsrc, const rb_source *src, rb_srcset **out) {
+  if (!ctx || !src || !out || nsrc < 1 || (ncomp != 1 && ncomp != 2)) {
+    rb_set_error("rb_srcset_create: bad argument");
+    return RB_ERR_ARG;
+  }
+  *out = nullptr;
+  for (int i = 0; i < nsrc; ++i) {
+    const int rc = check_source(ctx, src[i]);
+    if (rc != RB_OK) return rc;
+  }
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  rb_srcset *set = new rb_srcset();
+  set->ctx = ctx;
+  set->ncomp = ncomp;
+  set->nsrc = nsrc;
+  set->h.assign(src, src + nsrc);
+  if (cudaMalloc(&set->d, sizeof(rb_source) * nsrc) != cudaSuccess ||
+      cudaMemcpy(set->d, set->h.data(), sizeof(rb_source) * nsrc, cudaMemcpyHostToDevice) != cudaSuccess) {
+    rb_set_error("rb_srcset_create: device allocation failed");
+    if (set->d) cudaFree(set->d);
+    delete set;
+    return RB_ERR_CUDA;
+  }
+  *out = set;
+  return RB_OK;
+}
+
+void rb_srcset_destroy(rb_srcset *set) {
+  if (!set) return;
+  if (set->d) {
+    cudaSetDevice(set->ctx->device);
+    cudaFree(set->d);
+  }
+  delete set;
+}
+
+int rb_lnprob_src_dev(rb_ctx *ctx, const rb_srcset *set, int64_t n, const double *P, const int32_t *src_id,
+                      const rb_opts *opts, double *lnp, int64_t *nsolves_dev) {
+  if (!ctx || !set || set->ctx != ctx) {
+    rb_set_error("rb_lnprob_src_dev: the source set belongs to another context");
+    return RB_ERR_ARG;
+  }
+  if (set->nsrc > 1 && !src_id && n > 0) {
+    rb_set_error("rb_lnprob_src_dev: src_id is required with more than one source");
+    return RB_ERR_ARG;
+  }
+  int rc = lnprob_core(ctx, set->ncomp, n, P, set->d, set->nsrc, set->h[0], src_id, opts, lnp);
+  if (rc != RB_OK || n == 0) return rc;
+  return copy_nsolves(ctx, nsolves_dev);
+}
+
+// ---- stretch move, second form ----------------------------------------------------------------------------------
+static int make_split(const rb_split *sp, int64_t gid_base, int64_t nlocal, int32_t ndim, st2::SplitDev *out) {
+  if (!sp || sp->nwalkers < 2 || sp->walkers_per_source < 2 || sp->block < 2 || (sp->block & 1) ||
+      sp->block > (1LL << 30) || sp->nwalkers % sp->walkers_per_source || sp->walkers_per_source % sp->block ||
+      gid_base < 0 || nlocal < 0 || gid_base % sp->block || nlocal % sp->block || gid_base + nlocal > sp->nwalkers ||
+      ndim < 1) {
+    rb_set_error("rb_stretch: bad split (need block | walkers_per_source | nwalkers, block even, block | gid_base, nlocal)");
+    return RB_ERR_ARG;
+  }
+  out->W = sp->walkers_per_source;
+  out->B = (int)sp->block;
+  int w = 1;
+  while ((1LL << w) < sp->block) ++w;
+  out->w = w;
+  out->randomize = sp->randomize != 0;
+  st2::split_key_words(sp->seed, out->k0, out->k1);
+  return RB_OK;
+}
+
+int rb_stretch_pack_dev(rb_ctx *ctx, const rb_split *split, uint64_t step, int32_t half, int64_t gid_base,
+                        int64_t nlocal, int32_t ndim, const double *X, double *Chalf) {
+  st2::SplitDev sp;
+  if (!ctx || !X || !Chalf || (half != 0 && half != 1)) {
+    rb_set_error("rb_stretch_pack_dev: bad argument");
+    return RB_ERR_ARG;
+  }
+  int rc = make_split(split, gid_base, nlocal, ndim, &sp);
+  if (rc != RB_OK) return rc;
+  const long long nhalf = nlocal / 2;
+  if (nhalf == 0) return RB_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int tpb = 128;
+  st2::k_pack<<<(unsigned)((nhalf + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(sp, nullptr, step, half, gid_base, nhalf, ndim, X, Chalf);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+int rb_stretch_propose2_dev(rb_ctx *ctx, const rb_split *split, uint64_t step, int32_t half, int64_t gid_base,
+                            int64_t nlocal, int32_t ndim, const double *X, const double *Call, double a, double *Q,
+                            double *logfac, int32_t *src_id) {
+  st2::SplitDev sp;
+  if (!ctx || !X || !Call || !Q || !logfac || !(a > 1.0) || (half != 0 && half != 1)) {
+    rb_set_error("rb_stretch_propose2_dev: bad argument");
+    return RB_ERR_ARG;
+  }
+  int rc = make_split(split, gid_base, nlocal, ndim, &sp);
+  if (rc != RB_OK) return rc;
+  const long long nhalf = nlocal / 2;
+  if (nhalf == 0) return RB_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int tpb = 128;
+  st2::k_propose2<<<(unsigned)((nhalf + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(sp, nullptr, step, half, gid_base, nhalf, ndim, X,
+                                                                                 Call, a, split->seed, Q, logfac, src_id);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+int rb_stretch_accept2_dev(rb_ctx *ctx, const rb_split *split, uint64_t step, int32_t half, int64_t gid_base,
+                           int64_t nlocal, int32_t ndim, double *X, double *lnp, const double *Q, const double *lnp_new,
+                           const double *logfac, int64_t *naccept, int64_t *nan_count) {
+  st2::SplitDev sp;
+  if (!ctx || !X || !lnp || !Q || !lnp_new || !logfac || (half != 0 && half != 1)) {
+    rb_set_error("rb_stretch_accept2_dev: bad argument");
+    return RB_ERR_ARG;
+  }
+  int rc = make_split(split, gid_base, nlocal, ndim, &sp);
+  if (rc != RB_OK) return rc;
+  const long long nhalf = nlocal / 2;
+  if (nhalf == 0) return RB_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int tpb = 128;
+  st2::k_accept2<<<(unsigned)((nhalf + tpb - 1) / tpb), tpb, 0, ctx->stream>>>(
+      sp, nullptr, step, half, gid_base, nhalf, ndim, X, lnp, Q, lnp_new, logfac, split->seed,
+      reinterpret_cast<long long *>(naccept), reinterpret_cast<unsigned long long *>(nan_count), nullptr, nullptr);
+  CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  return RB_OK;
+}
+
+// One stretch-move step (both half-steps) on ctx->stream; the step index is *d_step + 0 (device-resident, so that the
+// captured graph of one step can be replayed).
+static int stretch_one_step(rb_ctx *ctx, const rb_srcset *set, const st2::SplitDev &sp, const rb_split *split, double a,
+                            const rb_opts *opts, long long N, int ndim, double *X, double *lnp, long long *naccept,
+                            unsigned long long *counters, double *Cbuf, double *Q, double *logfac, double *lnp_new,
+                            int *src_id, unsigned long long *d_step) {
+  const long long nhalf = N / 2;
+  const int tpb = 128;
+  const unsigned nb = (unsigned)((nhalf + tpb - 1) / tpb);
+  cudaStream_t s = ctx->stream;
+  for (int half = 0; half < 2; ++half) {
+    st2::k_pack<<<nb, tpb, 0, s>>>(sp, d_step, 0, 1 - half, 0, nhalf, ndim, X, Cbuf);
+    st2::k_propose2<<<nb, tpb, 0, s>>>(sp, d_step, 0, half, 0, nhalf, ndim, X, Cbuf, a, split->seed, Q, logfac, src_id);
+    int rc = lnprob_core(ctx, set->ncomp, nhalf, Q, set->d, set->nsrc, set->h[0], src_id, opts, lnp_new);
+    if (rc != RB_OK) return rc;
+    st2::k_accept2<<<nb, tpb, 0, s>>>(sp, d_step, 0, half, 0, nhalf, ndim, X, lnp, Q, lnp_new, logfac, split->seed, naccept,
+                                      counters, ctx->counters + 2, counters ? counters + 1 : nullptr);
+    ctx->launches += 3;
+  }
+  st2::k_step_inc<<<1, 1, 0, s>>>(d_step);
+  ctx->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return RB_OK;
+}
+
+int rb_stretch_run_dev(rb_ctx *ctx, const rb_srcset *set, const rb_split *split, double a, uint64_t step0,
+                       int64_t nsteps, const rb_opts *opts, double *X, double *lnp, int64_t *naccept,
+                       int64_t *counters, int32_t thin, double *chain, double *lnp_chain) {
+  if (!ctx || !set || set->ctx != ctx || !split || !X || !lnp || nsteps < 0 || !(a > 1.0) || thin < 1) {
+    rb_set_error("rb_stretch_run_dev: bad argument");
+    return RB_ERR_ARG;
+  }
+  const long long N = split->nwalkers;
+  const int ndim = 4 * set->ncomp;
+  st2::SplitDev sp;
+  int rc = make_split(split, 0, N, ndim, &sp);
+  if (rc != RB_OK) return rc;
+  if (N / split->walkers_per_source != set->nsrc) {
+    rb_set_error("rb_stretch_run_dev: nwalkers / walkers_per_source must equal the number of sources");
+    return RB_ERR_ARG;
+  }
+  if (nsteps == 0) return RB_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const long long nhalf = N / 2;
+  const size_t b_c = align256((size_t)nhalf * ndim * sizeof(double)), b_v = align256((size_t)nhalf * sizeof(double));
+  const size_t b_i = align256((size_t)nhalf * sizeof(int));
+  const size_t b_all = 2 * b_c + 2 * b_v + b_i + 256;
+  if (b_all > ctx->samp_bytes) {
+    if (ctx->samp_graph) {
+      cudaGraphExecDestroy(ctx->samp_graph);
+      ctx->samp_graph = nullptr;
+    }
+    if (ctx->samp_buf) cudaFree(ctx->samp_buf);
+    ctx->samp_buf = nullptr;
+    ctx->samp_bytes = 0;
+    CUDA_TRY(cudaMalloc(&ctx->samp_buf, b_all));
+    ctx->samp_bytes = b_all;
+  }
+  char *base = static_cast<char *>(ctx->samp_buf);
+  double *Cbuf = reinterpret_cast<double *>(base), *Q = reinterpret_cast<double *>(base + b_c);
+  double *logfac = reinterpret_cast<double *>(base + 2 * b_c), *lnp_new = reinterpret_cast<double *>(base + 2 * b_c + b_v);
+  int *src_id = reinterpret_cast<int *>(base + 2 * b_c + 2 * b_v);
+  unsigned long long *d_step = reinterpret_cast<unsigned long long *>(base + 2 * b_c + 2 * b_v + b_i);
+  cudaStream_t s = ctx->stream;
+  const unsigned long long step0_ = step0;
+  CUDA_TRY(cudaMemcpyAsync(d_step, &step0_, sizeof(step0_), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));   // step0_ lives on this stack frame
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(counters);
+  long long *nacc = reinterpret_cast<long long *>(naccept);
+  auto step_once = [&]() {
+    return stretch_one_step(ctx, set, sp, split, a, opts, N, ndim, X, lnp, nacc, cnt, Cbuf, Q, logfac, lnp_new,
+                            (set->nsrc > 1) ? src_id : nullptr, d_step);
+  };
+  auto store = [&](int64_t k) -> int {   // state after step k (0-based) -> chain slot
+    if ((k + 1) % thin) return RB_OK;
+    const int64_t slot = (k + 1) / thin - 1;
+    if (chain)
+      CUDA_TRY(cudaMemcpyAsync(chain + (size_t)slot * N * ndim, X, (size_t)N * ndim * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (lnp_chain)
+      CUDA_TRY(cudaMemcpyAsync(lnp_chain + (size_t)slot * N, lnp, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return RB_OK;
+  };
+  // A half-ensemble that fits one fused lnprob launch is latency-bound (config 1: 50 models per half-step): its step is
+  // captured once and replayed.  The key holds every argument the captured launches depend on.
+  const SolveCfg cfg = make_cfg(ctx, opts, 1.0, set->h[0].tbg, RB_GEOM_LVG);
+  const bool fused = !(set->nsrc == 1 && use_v2(ctx, opts) && cfg.sched && cfg.small && cfg.cache &&
+                       nhalf >= cfg.lnprob_pipe_min && nhalf * set->ncomp >= RB_SCHED_MIN);
+  int64_t k = 0;
+  if (fused && nsteps >= 3) {
+    struct Key {
+      const void *set, *X, *lnp, *naccept, *counters, *buf, *stream;
+      rb_split split;
+      rb_opts opts;
+      double a;
+    } key;
+    memset(&key, 0, sizeof(key));
+    key.set = set; key.X = X; key.lnp = lnp; key.naccept = naccept; key.counters = counters; key.buf = ctx->samp_buf;
+    key.stream = s; key.split = *split; key.a = a;
+    rb_default_opts(&key.opts);
+    if (opts) key.opts = *opts;
+    const unsigned char *kb = reinterpret_cast<const unsigned char *>(&key);
+    if (!ctx->samp_graph || ctx->samp_key.size() != sizeof(key) || memcmp(ctx->samp_key.data(), kb, sizeof(key)) != 0) {
+      if (ctx->samp_graph) {
+        cudaGraphExecDestroy(ctx->samp_graph);
+        ctx->samp_graph = nullptr;
+      }
+      rc = step_once();   // un-captured first step: every lazy allocation happens here
+      if (rc != RB_OK) return rc;
+      rc = store(k++);
+      if (rc != RB_OK) return rc;
+      cudaGraph_t g = nullptr;
+      const long long launches_before = ctx->launches;
+      CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      rc = step_once();
+      cudaError_t ce = cudaStreamEndCapture(s, &g);
+      ctx->launches = launches_before;   // nothing ran
+      if (rc != RB_OK || ce != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        if (rc == RB_OK) rb_set_error(std::string("rb_stretch_run_dev: graph capture failed: ") + cudaGetErrorString(ce));
+        return rc != RB_OK ? rc : RB_ERR_CUDA;
+      }
+      ce = cudaGraphInstantiate(&ctx->samp_graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) {
+        ctx->samp_graph = nullptr;
+        rb_set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+        return RB_ERR_CUDA;
+      }
+      ctx->samp_key.assign(kb, kb + sizeof(key));
+    }
+    const long long per_step = 2 * 4 + 1;   // pack, propose2, lnprob, accept2 per half-step + the step counter
+    for (; k < nsteps; ++k) {
+      CUDA_TRY(cudaGraphLaunch(ctx->samp_graph, s));
+      ctx->launches += per_step;
+      rc = store(k);
+      if (rc != RB_OK) return rc;
+    }
+    return RB_OK;
+  }
+  for (; k < nsteps; ++k) {
+    rc = step_once();
+    if (rc != RB_OK) return rc;
+    rc = store(k);
+    if (rc != RB_OK) return rc;
+  }
   return RB_OK;
 }
 

@@ -170,7 +170,7 @@ def prefit(ncomp, R, Jup, flux, eflux, bounds, p0, T_d=None, opts=None):
 
 
 def fit_source(source, data, ncomp=1, nwalkers=None, n_iter_burn=100, n_iter_walk=None, seed=20170914,
-               device=0, datapath=None, opts=None, outdir=None, store_chain=True):
+               device=0, datapath=None, opts=None, outdir=None, store_chain=True, allow_synthetic=False):
     """One pass of the reference's per-source loop.  Returns a dict with every item of the pickle plus
     the percentile summaries and the sampler's acceptance fraction."""
     from .radex import Radex
@@ -190,6 +190,13 @@ def fit_source(source, data, ncomp=1, nwalkers=None, n_iter_burn=100, n_iter_wal
     R = Radex(species="co", datapath=datapath,
               density={"oH2": mod.fortho * 1e10, "pH2": (1 - mod.fortho) * 1e10}, column=1e6, temperature=20.0,
               tbackground=tbg, deltav=1.0, escapeProbGeom="lvg", device=device)
+    if R.molfile_is_synthetic and not allow_synthetic:
+        raise ValueError(
+            "%s is the synthetic CO-like table shipped for tests (made-up collision rates): posteriors fitted with it are "
+            "not physical.  Pass datapath= (or --datapath / RADEX_DATAPATH) pointing at the directory that holds the LAMDA "
+            "co.dat, as the reference's radex_moldata/ does, or allow_synthetic=True (--allow-synthetic)." % R.molpath)
+    if R.molfile_is_synthetic:
+        logger.warning("fitting with the SYNTHETIC molecular table %s: results are not physical", R.molpath)
     popt, pcov, pmin, info = prefit(ncomp, R, Jup, flux, eflux, bounds, p0, T_d=T_d, opts=opts)
 
     ndim = 4 * ncomp
@@ -208,8 +215,11 @@ def fit_source(source, data, ncomp=1, nwalkers=None, n_iter_burn=100, n_iter_wal
     theta_med = np.percentile(flatchain, 50, axis=0)
     result = dict(source=source, z=z, bounds=bounds, T_d=T_d, data=(Jup, flux, eflux), popt=popt, pcov=pcov,
                   pmin=pmin, theta_med=theta_med, chain=chain, lnprobability=lnprobability,
-                  summary=posterior_summary(flatchain, ncomp), acceptance_fraction=sampler.acceptance_fraction,
-                  prefit_info=info, solves=int(eng.total_solves.item()))
+                  summary=posterior_summary(flatchain, ncomp),
+                  acceptance_fraction=float(np.mean(sampler.acceptance_fraction)),
+                  acceptance_fraction_per_walker=sampler.acceptance_fraction,
+                  prefit_info=info, solves=int(eng.total_solves.item()) + sampler.total_solves,
+                  molfile=R.molpath, molfile_synthetic=R.molfile_is_synthetic)
     if outdir is not None:
         os.makedirs(outdir, exist_ok=True)
         if ncomp == 1:     # emcee_radex.py:504-509
@@ -250,6 +260,10 @@ def main(argv=None):
     ap.add_argument("--burn", type=int, default=100)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--seed", type=int, default=20170914)
+    ap.add_argument("--datapath", default=None, help="directory holding the LAMDA co.dat (the reference's radex_moldata/); "
+                                                     "default: $RADEX_DATAPATH")
+    ap.add_argument("--allow-synthetic", action="store_true",
+                    help="fit with the synthetic test table shipped in the package (NOT physical)")
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -262,7 +276,8 @@ def main(argv=None):
     for source in sources[rank::world]:          # replicas only: one source per GPU at a time, no communication
         logger.info("Processing %s on GPU %d", source, device)
         res = fit_source(source, data, ncomp=args.ncomp, nwalkers=args.walkers, n_iter_burn=args.burn,
-                         n_iter_walk=args.steps, seed=args.seed, device=device, outdir=outdir)
+                         n_iter_walk=args.steps, seed=args.seed, device=device, outdir=outdir, datapath=args.datapath,
+                         allow_synthetic=args.allow_synthetic)
         print_summary(res, args.ncomp)
 
 

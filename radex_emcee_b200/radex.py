@@ -38,6 +38,16 @@ def _unitless(x):
     return x.value if hasattr(x, "value") else x
 
 
+def is_synthetic_table(molpath: str) -> bool:
+    """True for the CO-like table synth_lamda.py writes (its !MOLECULE line says so): good for tests, not for science."""
+    try:
+        with open(molpath, "r", errors="replace") as f:
+            head = [next(f, "") for _ in range(3)]
+    except OSError:
+        return False
+    return any("synthetic" in ln.lower() for ln in head)
+
+
 _mol_cache: dict = {}
 _ctx_cache: dict = {}
 
@@ -133,6 +143,7 @@ class Radex:
                              "  Current path is {0}".format(molpath))
         self._species = species
         self.molpath = molpath
+        self.molfile_is_synthetic = is_synthetic_table(molpath)
         self.mol = get_moldata(molpath)        # host parse only; the GPU context is created on first use
         ids = {v: k for k, v in _COLLIDER_IDS.items()}
         self._valid_colliders = [_CANON[ids[int(i)]] for i in self.mol.partner_id]

@@ -16,6 +16,34 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu)")
 
 
+def _gpu_unavailable():
+    """Reason the `gpu` tests cannot run here, or None.  (libradex_b200.so is built for sm_100a only.)"""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return "no CUDA device"
+        if torch.cuda.get_device_capability(0)[0] < 10:
+            return "libradex_b200.so is built for sm_100a; device is sm_%d%d" % torch.cuda.get_device_capability(0)
+    except Exception as e:      # pragma: no cover
+        return "torch unusable: %s" % e
+    if not os.path.exists(os.path.join(ROOT, "radex_emcee_b200", "libradex_b200.so")):
+        return "libradex_b200.so is not built (python -m radex_emcee_b200.build)"
+    return None
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a machine without a B200 skips the gpu tests instead of failing them.  With an
+    explicit `-m gpu` they run regardless, so a GPU box with a broken build fails loudly instead of skipping."""
+    if "gpu" in (config.getoption("-m") or ""):
+        return
+    why = _gpu_unavailable()
+    if why:
+        skip = pytest.mark.skip(reason=why)
+        for it in items:
+            if "gpu" in it.keywords:
+                it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def molfile():
     return MOLFILE

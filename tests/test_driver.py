@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from radex_emcee_b200 import driver
-from radex_emcee_b200.data import DATA_DIR, read_data
+from radex_emcee_b200.data import DATA_DIR, get_source, read_data
 
 
 def test_forward_steps_follow_scipy_two_point_rule():
@@ -57,8 +57,12 @@ def test_summaries():
 @pytest.mark.parametrize("ncomp", [1, 2])
 def test_fit_source_end_to_end(tmp_path, ncomp):
     data = read_data(os.path.join(DATA_DIR, "flux.dat" if ncomp == 1 else "flux_for2p.dat"))
+    with pytest.raises(ValueError, match="synthetic"):       # the shipped table is for tests: refuse unless told
+        driver.fit_source("G09v1.97", data, ncomp=ncomp, nwalkers=64, n_iter_burn=1, n_iter_walk=1)
     res = driver.fit_source("G09v1.97", data, ncomp=ncomp, nwalkers=64, n_iter_burn=10, n_iter_walk=20,
-                            outdir=str(tmp_path))
+                            outdir=str(tmp_path), allow_synthetic=True)
+    assert res["molfile_synthetic"] and res["molfile"].endswith("co.dat")
+    assert res["acceptance_fraction_per_walker"].shape == (64,)
     b = res["bounds"]
     assert np.all((res["popt"] >= b[:, 0]) & (res["popt"] <= b[:, 1]))
     assert np.all((res["pmin"] >= b[:, 0]) & (res["pmin"] <= b[:, 1]))
@@ -82,3 +86,37 @@ def test_fit_source_end_to_end(tmp_path, ncomp):
     buf = io.StringIO()
     driver.print_summary(res, ncomp, file=buf)
     assert buf.getvalue().count("xxx:") >= 7
+
+
+@pytest.mark.gpu
+def test_prefit_matches_scipy_on_the_oracle_model(oracle):
+    """the pre-sampling optimisers decide the walkers' starting ball.  driver.prefit (GPU model,
+    batched finite differences with scipy's own step rules) against plain scipy on the CPU oracle's model_lvg / lnprob
+    (emcee_radex.py:444-467: curve_fit with bounds -> trf with a 2-point Jacobian; minimize -> L-BFGS-B with its
+    numerical gradient), same starting point."""
+    from scipy.optimize import curve_fit, minimize
+    from radex_emcee_b200 import emcee_radex as er1
+    from radex_emcee_b200.radex import Radex
+    data = read_data(os.path.join(DATA_DIR, "flux.dat"))
+    for name in ("G09v1.97", "NCv1.143"):
+        z, lw, Jup, flux, eflux = get_source(name, data)
+        tbg, _ra, bounds, p0 = er1.source_setup(z)
+        lo, hi = bounds[:, 0], bounds[:, 1]
+        R = Radex(species="co", density={"oH2": 7.5e9, "pH2": 2.5e9}, column=1e6, temperature=20.0, tbackground=tbg)
+        popt, pcov, pmin, info = driver.prefit(1, R, Jup, flux, eflux, bounds, p0)
+
+        def model_cpu(_x, *p):
+            p = np.asarray(p)
+            n = 10.0 ** p[0]
+            r = oracle.solve_batch([10.0 ** p[1]], [0.25 * n], [0.75 * n], [10.0 ** p[2]], tbg=tbg)
+            return r["surf"][0][np.asarray(Jup) - 1] * 10.0 ** p[3] * 1e23
+
+        popt_ref, _ = curve_fit(model_cpu, Jup, flux, sigma=eflux, p0=p0, bounds=(lo, hi))
+        chi2 = lambda p: float(np.sum(((flux - model_cpu(None, *p)) / eflux) ** 2))
+        # same minimum: chi^2 to 1e-3 relative and the parameters to 0.01 dex along well-constrained directions
+        assert chi2(popt) == pytest.approx(chi2(popt_ref), rel=1e-3, abs=1e-6), (name, popt, popt_ref)
+        assert np.abs(popt - popt_ref).max() < 0.05, (name, popt, popt_ref)
+        nll = lambda p: -oracle.lnprob1(p, Jup, flux, eflux, bounds, tbg)
+        res = minimize(nll, popt_ref, bounds=list(zip(lo, hi)), method="L-BFGS-B")
+        assert nll(pmin) == pytest.approx(res.fun, rel=1e-3, abs=1e-4), (name, pmin, res.x)
+        assert np.abs(pmin - res.x).max() < 0.05, (name, pmin, res.x)

@@ -257,14 +257,9 @@ def test_ordered_launches_without_half_warp_engine_are_bit_identical(ctx):
         itr, _ = ctx.counters()
         sr = ctx.cache_stats()
         # kernel 0 twice: half-warp engines only (batches < 2^18), then with the 20/24/28-level lead blocks in
-        # their own launches as well (forced here through the A/B switch RB_PARK_MAX)
-        for kernel, park_max in ((0, None), (0, "7"), (4, None)):
-            if park_max is not None:
-                os.environ["RB_PARK_MAX"] = park_max
-            try:
-                a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, kernel=kernel, **kw)
-            finally:
-                os.environ.pop("RB_PARK_MAX", None)
+        # their own launches as well (forced here through rb_opts.park_max)
+        for kernel, park_max in ((0, None), (0, 7), (4, None)):
+            a = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, kernel=kernel, park_max=park_max, **kw)
             ita, _ = ctx.counters()
             assert ita == itr, (kernel, park_max, kw, ita, itr)
             assert tuple(ctx.cache_stats()) == tuple(sr), (kernel, park_max, kw)
