@@ -286,6 +286,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=20)
     ap.add_argument("--stop", default="pyradex", choices=["pyradex", "radex"])
+    ap.add_argument("--abs-tol", type=float, default=1e-16, help="pyradex stop rule: run_radex's abs_convergence_threshold (core.py:857)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline and the oracle-side parity record")
     ap.add_argument("--no-extras", action="store_true", help="skip the parity / stop_radex / sampler records")
@@ -303,7 +304,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n = 1 << args.log2n
     stop_rule = 0 if args.stop == "pyradex" else 1
-    config = make_config(args.log2n, args.stop)
+    config = make_config(args.log2n, args.stop if args.abs_tol == 1e-16 else "%s(abs_tol=%g)" % (args.stop, args.abs_tol))
     cores = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -356,7 +357,7 @@ def main():
     d_it = torch.empty(n, dtype=torch.int32, device=dev)
     d_st = torch.empty(n, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    opts = _lib.default_opts(stop_rule=stop_rule, kernel=args.kernel)
+    opts = _lib.default_opts(stop_rule=stop_rule, kernel=args.kernel, abs_tol=args.abs_tol)
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
 
@@ -452,7 +453,7 @@ def main():
 
     # ---- extra records: every rank takes part in the collective ones ---------------------------------------
     extras = {}
-    if not args.no_extras and not args.keep and args.kernel == 0:
+    if not args.no_extras and not args.keep and args.kernel == 0 and args.abs_tol == 1e-16:
         # (1) the same sweep under the other stop rule, against the arrays of the timed launch
         other = 1 - stop_rule
         o2 = _lib.default_opts(stop_rule=other, kernel=args.kernel)
@@ -560,7 +561,7 @@ def main():
         }
         line.update(extras)
         if not args.no_cpu and not args.keep:
-            if stop_rule == 0 and npar > 0:
+            if stop_rule == 0 and npar > 0 and args.abs_tol == 1e-16:
                 line["parity"] = parity_record(npar, tk, nh2, cd, par_arrays)
             if world == 1:
                 v, sample, dt, _ = cpu_reference(tk, nh2, cd, stop_rule, args.cpu_seconds, 1)

@@ -30,6 +30,7 @@ from oracle import macho_ref  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402
 
 MOLFILE = os.path.join(ROOT, "radex_emcee_b200", "data", "co.dat")
+ROTOR = os.path.join(ROOT, "radex_emcee_b200", "data", "rotor21.dat")
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
@@ -128,6 +129,51 @@ def main():
     print("cases", len(cases), "niter", res["niter"])
     print("chain niter", chain["niter"])
     print("imports the binary called:", sorted(set(r.img.calls)))
+    make_rotor(rng)
+
+
+def make_rotor(rng):
+    """macho_solve_rotor21.npz: the same loop through the binary for the second synthetic table (21 levels, partners
+    H2 and e on their own temperature grids): pins matrix()/lubksb for a matrix size other than CO's and for the
+    collider mix of SURVEY.md 8(f) rank 4."""
+    o = Oracle(ROTOR)
+    r = macho_ref.RefRadex()
+    r.load_tables(o.nlev, o.nline, o.eterm, o.gstat, o.iupp, o.ilow, o.aeinst, o.xnu, o.spfreq, o.eup)
+    nl, nn = o.nlev, o.nline
+    cases = []
+    for tbg, method, k in ((2.7315, 2, 12), (10.926, 2, 8), (2.7315, 1, 5), (2.7315, 3, 5)):
+        for _ in range(k):
+            lt, ln, lN = rng.uniform(np.log10(max(tbg, 5.0)), 2.7), rng.uniform(2.5, 7.0), rng.uniform(11.5, 15.5)
+            ne = 0.0 if rng.uniform() < 0.3 else 10 ** rng.uniform(-2.0, 2.0)
+            cases.append((10 ** lt, 10 ** ln, ne, 10 ** lN, tbg, method))
+    cases = np.array(cases)
+    res = dict(xpop=[], tex=[], tau=[], niter=[], crate=[])
+    xr, tr, ur = r.dview("xpop", macho_ref.MAXLEV), r.dview("tex", macho_ref.MAXLINE), r.dview("taul", macho_ref.MAXLINE)
+    for (T, n, ne, N, tbg, method) in cases:
+        d7 = np.array([n, 0, 0, ne, 0, 0, 0.0])
+        o.set_physics_dens(T, d7)
+        r.load_rates(o.crate, o.ctot, o.totdens)
+        r.backrad(tbg)
+        r.set_scalar("tkin", T)
+        r.set_scalar("cdmol", N)
+        r.set_scalar("deltav", 1e5)
+        r.set_int("method", int(method))
+        d = r.dview("density", 9)
+        d[:] = 0
+        d[:7] = d7
+        # fresh state per case, as a new Radex object has it
+        xr[:nl] = 0
+        tr[:nn] = 0
+        ur[:nn] = 0
+        res["niter"].append(r.run_pyradex_loop(reuse_last=False))
+        res["xpop"].append(xr[:nl].copy())
+        res["tex"].append(tr[:nn].copy())
+        res["tau"].append(ur[:nn].copy())
+        res["crate"].append(o.crate.copy())
+    np.savez_compressed(os.path.join(OUT, "macho_solve_rotor21.npz"), cases=cases, niter=np.array(res["niter"]),
+                        xpop=np.array(res["xpop"]), tex=np.array(res["tex"]), tau=np.array(res["tau"]),
+                        crate=np.array(res["crate"]))
+    print("rotor21 cases", len(cases), "niter", res["niter"])
 
 
 if __name__ == "__main__":

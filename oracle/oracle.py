@@ -81,6 +81,10 @@ def lib():
         L.ro_solve_batch.argtypes = [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int,
                                      C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                      _dp, _dp, _dp, _dp, _ip, _ip]
+        L.ro_solve_batch_dens.argtypes = [C.c_void_p, C.c_long, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int,
+                                          C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                          _dp, _dp, _dp, _dp, _ip, _ip]
+        L.ro_mol_get_partner_ids.argtypes = [C.c_void_p, _ip]
         _lib = L
     return _lib
 
@@ -159,6 +163,11 @@ class Oracle:
         d = np.array([n_h2, n_ph2, n_oh2, 0, 0, 0, 0], dtype=np.float64)
         self.L.ro_set_physics(self.st, float(tkin), _d(d), 7)
 
+    def set_physics_dens(self, tkin, dens7):
+        d = np.ascontiguousarray(dens7, dtype=np.float64)
+        assert d.shape == (7,)
+        self.L.ro_set_physics(self.st, float(tkin), _d(d), 7)
+
     def set_column(self, cdmol, deltav_kms=1.0):
         self.L.ro_state_set_column(self.st, float(cdmol), float(deltav_kms) * 1e5)
 
@@ -194,6 +203,27 @@ class Oracle:
                               stop_rule, miniter, maxiter, abs_tol, fk, thc, _d(out["xpop"]), _d(out["tex"]),
                               _d(out["tau"]), _d(out["surf"]), _i(out["niter"]), _i(out["status"]))
         return out
+
+    def solve_batch_dens(self, tkin, dens7, cdmol, deltav_kms=1.0, tbg=2.7315, method=2,
+                         stop_rule=STOP_PYRADEX, miniter=10, maxiter=200, abs_tol=1e-16,
+                         fk=FK_ASTROPY, thc=THC_ASTROPY):
+        """dens7[n, 7]: one density per LAMDA partner id 1..7 (H2, p-H2, o-H2, e, H, He, H+), as pyradex writes
+        cphys.density (core.py:525-561)."""
+        tkin, cdmol = (np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64) for x in (tkin, cdmol))
+        n = tkin.size
+        dens7 = np.ascontiguousarray(np.broadcast_to(np.asarray(dens7, dtype=np.float64), (n, 7)))
+        out = dict(xpop=np.zeros((n, self.nlev)), tex=np.zeros((n, self.nline)), tau=np.zeros((n, self.nline)),
+                   surf=np.zeros((n, self.nline)), niter=np.zeros(n, np.int32), status=np.zeros(n, np.int32))
+        self.L.ro_solve_batch_dens(self.st, n, _d(tkin), _d(dens7), _d(cdmol), deltav_kms, tbg, method, stop_rule,
+                                   miniter, maxiter, abs_tol, fk, thc, _d(out["xpop"]), _d(out["tex"]), _d(out["tau"]),
+                                   _d(out["surf"]), _i(out["niter"]), _i(out["status"]))
+        return out
+
+    @property
+    def partner_ids(self):
+        ids = np.zeros(self.L.ro_mol_npart(self.mol), np.int32)
+        self.L.ro_mol_get_partner_ids(self.mol, _i(ids))
+        return ids
 
     def lnprob1(self, p, jup, flux, eflux, bounds, tbg, stop_rule=STOP_PYRADEX, miniter=10, maxiter=200,
                 abs_tol=1e-16, fk=FK_ASTROPY, thc=THC_ASTROPY):

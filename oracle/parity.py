@@ -31,8 +31,13 @@ MORE_PERTURBATIONS = ((1, -3e-13), (0, 1e-11), (2, 3e-12), (1, 1e-10), (0, -1e-1
 
 def solve_threads(molfile, T, nh2, N, tbg, method=2, nthreads=None, **kw):
     """Oracle.solve_batch over the host cores (one RADEX COMMON-block state per thread; ctypes drops the GIL).
-    Every solve starts clean, so the result does not depend on the split."""
-    T, nh2, N = (np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64) for a in (T, nh2, N))
+    Every solve starts clean, so the result does not depend on the split.  nh2: total n(H2), split 1:3 into p-/o-H2
+    like the drivers (opr = 3) -- or an [n, 7] array with one density per LAMDA partner id (H2, p-H2, o-H2, e, H, He, H+)."""
+    T, N = (np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64) for a in (T, N))
+    nh2 = np.ascontiguousarray(nh2, dtype=np.float64)
+    if nh2.ndim == 2:
+        return _solve_threads_dens(molfile, T, nh2, N, tbg, method, nthreads, **kw)
+    nh2 = np.atleast_1d(nh2)
     n = T.size
     nthreads = max(1, min(nthreads or (os.cpu_count() or 1), 64, n))
     chunks = np.array_split(np.arange(n), nthreads)
@@ -41,6 +46,23 @@ def solve_threads(molfile, T, nh2, N, tbg, method=2, nthreads=None, **kw):
     def work(t):
         i = chunks[t]
         return oracles[t].solve_batch(T[i], 0.25 * nh2[i], 0.75 * nh2[i], N[i], tbg=tbg, method=method, **kw)
+
+    with ThreadPoolExecutor(nthreads) as ex:
+        parts = list(ex.map(work, range(nthreads)))
+    out = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    out["iupp"] = oracles[0].iupp.copy()
+    return out
+
+
+def _solve_threads_dens(molfile, T, dens7, N, tbg, method, nthreads, **kw):
+    n = T.size
+    nthreads = max(1, min(nthreads or (os.cpu_count() or 1), 64, n))
+    chunks = np.array_split(np.arange(n), nthreads)
+    oracles = [Oracle(molfile) for _ in range(nthreads)]
+
+    def work(t):
+        i = chunks[t]
+        return oracles[t].solve_batch_dens(T[i], dens7[i], N[i], tbg=tbg, method=method, **kw)
 
     with ThreadPoolExecutor(nthreads) as ex:
         parts = list(ex.map(work, range(nthreads)))
@@ -74,7 +96,8 @@ def worst(got, ref, iupp):
 def classify(molfile, T, nh2, N, tbg, method=2, ref=None, nthreads=None, more=False, **kw):
     """Oracle-only classification.  Returns (ref, classes, runs): classes maps name -> bool mask (exclusive, in the
     order nonfinite, maser, sensitive, well_posed); runs = the perturbed oracle results (for attractor_error)."""
-    T, nh2, N = (np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64) for a in (T, nh2, N))
+    T, N = (np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64) for a in (T, N))
+    nh2 = np.ascontiguousarray(nh2, dtype=np.float64)      # [n] total n(H2), or [n, 7] per partner id
     if ref is None:
         ref = solve_threads(molfile, T, nh2, N, tbg, method, nthreads, **kw)
     iupp = ref["iupp"] if "iupp" in ref else Oracle(molfile).iupp

@@ -159,6 +159,7 @@ ro_mol *ro_mol_load(const char *path) {
 int ro_mol_nlev(const ro_mol *m) { return m->nlev; }
 int ro_mol_nline(const ro_mol *m) { return m->nline; }
 int ro_mol_npart(const ro_mol *m) { return m->npart; }
+void ro_mol_get_partner_ids(const ro_mol *m, int *ids) { for (int p = 0; p < m->npart; ++p) ids[p] = m->part_id[p]; }
 void ro_mol_get_levels(const ro_mol *m, double *eterm, double *gstat) {
   memcpy(eterm, m->eterm, sizeof(double) * m->nlev);
   memcpy(gstat, m->gstat, sizeof(double) * m->nlev);
@@ -538,15 +539,14 @@ void ro_surface_brightness(const ro_state *s, double fk_epi, double thc_epi, dou
  * Mirrors set_params(density={'oH2','pH2'}, column, temperature) + run_radex + epilogue
  * (emcee/emcee_radex.py:120-128).  status bits: 1 T range, 2 N range (the ValueErrors of
  * core.py:734-735,771-772), 4 hit maxiter, 8 non-finite output.                               */
-int ro_solve(ro_state *s, double tkin, double n_ph2, double n_oh2, double cdmol, double deltav_kms,
-             double tbg, int method, int stop_rule, int miniter, int maxiter, double abs_tol,
-             double fk_epi, double thc_epi, double *surf, int *niter_out) {
+int ro_solve_dens(ro_state *s, double tkin, const double *dens7, double cdmol, double deltav_kms,
+                  double tbg, int method, int stop_rule, int miniter, int maxiter, double abs_tol,
+                  double fk_epi, double thc_epi, double *surf, int *niter_out) {
   int status = 0;
   if (!(tkin > 0.0 && tkin <= 1e4)) status |= 1;
   if (!(cdmol >= 1e5 && cdmol <= 1e25)) status |= 2;
   if (status) { if (niter_out) *niter_out = 0; return status; }
-  double dens[7] = {0.0, n_ph2, n_oh2, 0, 0, 0, 0};
-  ro_set_physics(s, tkin, dens, 7);
+  ro_set_physics(s, tkin, dens7, 7);
   s->cdmol = cdmol;
   s->deltav = deltav_kms * 1e5;
   s->method = method;
@@ -559,6 +559,22 @@ int ro_solve(ro_state *s, double tkin, double n_ph2, double n_oh2, double cdmol,
     for (int l = 0; l < s->mol->nline; ++l) if (!isfinite(surf[l])) status |= 8;
   }
   return status;
+}
+
+/* density={'oH2': .., 'pH2': ..} as the drivers set it (emcee/emcee_radex.py:122-124): pyradex's density setter
+ * folds the two into n(H2) when the molecular file lists H2 itself as a partner, and keeps them apart otherwise
+ * (emcee/pyradex/core.py:551-556).                                                                            */
+int ro_solve(ro_state *s, double tkin, double n_ph2, double n_oh2, double cdmol, double deltav_kms,
+             double tbg, int method, int stop_rule, int miniter, int maxiter, double abs_tol,
+             double fk_epi, double thc_epi, double *surf, int *niter_out) {
+  double dens[7] = {0.0, n_ph2, n_oh2, 0, 0, 0, 0};
+  for (int p = 0; p < s->mol->npart; ++p)
+    if (s->mol->part_id[p] == 1) {
+      dens[0] = n_ph2 + n_oh2;
+      dens[1] = dens[2] = 0.0;
+    }
+  return ro_solve_dens(s, tkin, dens, cdmol, deltav_kms, tbg, method, stop_rule, miniter, maxiter, abs_tol, fk_epi,
+                       thc_epi, surf, niter_out);
 }
 
 /* lnlike (emcee/emcee_radex.py:132-167; emcee_radex_2comp.py:169-196): model[] already in Jy km/s. */
@@ -673,6 +689,28 @@ void ro_solve_batch(ro_state *s, long n, const double *tkin, const double *n_ph2
     if (tex) memcpy(tex + i * nn, s->tex, sizeof(double) * nn);
     if (tau) memcpy(tau + i * nn, s->taul, sizeof(double) * nn);
     if (surf) memcpy(surf + i * nn, sb, sizeof(double) * nn);
+  }
+}
+
+/* the same with one density per LAMDA partner id (dens[i * 7 + id - 1]): any mix of H2, p-H2, o-H2, e, H, He, H+ */
+void ro_solve_batch_dens(ro_state *s, long n, const double *tkin, const double *dens7, const double *cdmol,
+                         double deltav_kms, double tbg, int method, int stop_rule, int miniter, int maxiter,
+                         double abs_tol, double fk_epi, double thc_epi, double *xpop, double *tex, double *tau,
+                         double *surf, int *niter, int *status) {
+  int nl = s->mol->nlev, nn = s->mol->nline;
+  double sb[4096];
+  for (long i = 0; i < n; ++i) {
+    int it = 0;
+    int st = ro_solve_dens(s, tkin[i], dens7 + 7 * i, cdmol[i], deltav_kms, tbg, method, stop_rule, miniter, maxiter,
+                           abs_tol, fk_epi, thc_epi, sb, &it);
+    if (status) status[i] = st;
+    if (niter) niter[i] = it;
+    for (int k = 0; k < nl; ++k) if (xpop) xpop[i * nl + k] = (st & 3) ? NAN : s->xpop[k];
+    for (int k = 0; k < nn; ++k) {
+      if (tex) tex[i * nn + k] = (st & 3) ? NAN : s->tex[k];
+      if (tau) tau[i * nn + k] = (st & 3) ? NAN : s->taul[k];
+      if (surf) surf[i * nn + k] = (st & 3) ? NAN : sb[k];
+    }
   }
 }
 

@@ -100,6 +100,7 @@ struct rb_ctx {
   bool ln_partners_ok = false;            // lnprob: the file has H2, or p-H2 / o-H2, as a collision partner
   void *samp_buf = nullptr;               // rb_stretch_run_dev: complementary half, proposals, their lnprob, step counter (grow-only)
   size_t samp_bytes = 0;
+  cudaEvent_t ev_samp = nullptr;
   cudaGraphExec_t samp_graph = nullptr;   // one stretch-move step, captured for the arguments in samp_key
   std::vector<unsigned char> samp_key;
   long long launches = 0;
@@ -1530,6 +1531,7 @@ void rb_ctx_destroy(rb_ctx *ctx) {
   if (ctx->src_one) cudaFree(ctx->src_one);
   if (ctx->samp_buf) cudaFree(ctx->samp_buf);
   if (ctx->samp_graph) cudaGraphExecDestroy(ctx->samp_graph);
+  if (ctx->ev_samp) cudaEventDestroy(ctx->ev_samp);
   for (cudaEvent_t ev : ctx->chunk_done) cudaEventDestroy(ev);
   for (int j = 0; j < 6; ++j) {
     if (ctx->side[j]) cudaStreamDestroy(ctx->side[j]);
@@ -2195,9 +2197,37 @@ static int stretch_one_step(rb_ctx *ctx, const rb_srcset *set, const st2::SplitD
   return RB_OK;
 }
 
+static int stretch_run_impl(rb_ctx *ctx, const rb_srcset *set, const rb_split *split, double a, uint64_t step0,
+                            int64_t nsteps, const rb_opts *opts, double *X, double *lnp, int64_t *naccept,
+                            int64_t *counters, int32_t thin, double *chain, double *lnp_chain);
+
 int rb_stretch_run_dev(rb_ctx *ctx, const rb_srcset *set, const rb_split *split, double a, uint64_t step0,
                        int64_t nsteps, const rb_opts *opts, double *X, double *lnp, int64_t *naccept,
                        int64_t *counters, int32_t thin, double *chain, double *lnp_chain) {
+  if (!ctx) {
+    rb_set_error("rb_stretch_run_dev: bad argument");
+    return RB_ERR_ARG;
+  }
+  // CUDA's legacy default stream (what PyTorch's default stream is) cannot be captured: the loop then runs on the
+  // ctx's own stream, ordered after the work already queued on the caller's stream and before what it queues next
+  cudaStream_t caller = ctx->stream;
+  if (caller != nullptr && caller != cudaStreamLegacy)
+    return stretch_run_impl(ctx, set, split, a, step0, nsteps, opts, X, lnp, naccept, counters, thin, chain, lnp_chain);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (!ctx->ev_samp) CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_samp, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(ctx->ev_samp, caller));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->own_stream, ctx->ev_samp, 0));
+  ctx->stream = ctx->own_stream;
+  const int rc = stretch_run_impl(ctx, set, split, a, step0, nsteps, opts, X, lnp, naccept, counters, thin, chain, lnp_chain);
+  ctx->stream = caller;
+  CUDA_TRY(cudaEventRecord(ctx->ev_samp, ctx->own_stream));
+  CUDA_TRY(cudaStreamWaitEvent(caller, ctx->ev_samp, 0));
+  return rc;
+}
+
+static int stretch_run_impl(rb_ctx *ctx, const rb_srcset *set, const rb_split *split, double a, uint64_t step0,
+                            int64_t nsteps, const rb_opts *opts, double *X, double *lnp, int64_t *naccept,
+                            int64_t *counters, int32_t thin, double *chain, double *lnp_chain) {
   if (!ctx || !set || set->ctx != ctx || !split || !X || !lnp || nsteps < 0 || !(a > 1.0) || thin < 1) {
     rb_set_error("rb_stretch_run_dev: bad argument");
     return RB_ERR_ARG;

@@ -111,9 +111,80 @@ def write_co_synth(path: str, nlev: int = 41) -> str:
     return path
 
 
+# ---- a second, differently shaped table for the general-molecule path -------------------------------------------
+# 21 levels of a heavier linear rotor ("CS-like": B = 0.8171 cm^-1, mu = 1.958 D), 20 lines, and two partners that
+# exercise what CO's table does not: H2 itself (LAMDA id 1: pyradex folds oH2 + pH2 into it, core.py:551-556) on a
+# 9-node temperature grid with every downward pair, and electrons (id 4) on a 6-node grid with |dJ| <= 3 only.
+ROTOR_B, ROTOR_D, ROTOR_MU = 0.8171, 1.43e-6, 1.958
+ROTOR_TEMPS_H2 = [10.0, 20.0, 40.0, 60.0, 100.0, 150.0, 200.0, 300.0, 500.0]
+ROTOR_TEMPS_E = [10.0, 30.0, 100.0, 300.0, 1000.0, 3000.0]
+
+
+def _rotor_rate(partner: int, jup: int, jlo: int, t: float) -> float:
+    dj = jup - jlo
+    if partner == 1:
+        return 6.5e-11 * math.exp(-0.45 * (dj - 1)) * (1.0 + t / 90.0) ** 0.25 / (1.0 + 0.02 * jup) * \
+            (1.15 if dj % 2 == 0 else 1.0)
+    # electrons: dipole-dominated, ~1e-6 cm^3/s, falling with dJ and slowly with T
+    return 2.4e-6 * (0.08 ** (dj - 1)) * (t / 100.0) ** -0.35 * (jup / (2.0 * jup + 1.0)) * (1.0 + 0.1 * math.exp(-jlo))
+
+
+def write_rotor_synth(path: str, nlev: int = 21) -> str:
+    """Write the 21-level synthetic rotor (partners H2 and e) to ``path``."""
+    lines = []
+    w = lines.append
+    w("!MOLECULE")
+    w("ROTOR21 (synthetic CS-like table, radex_emcee_b200.synth_lamda)")
+    w("!MOLECULAR WEIGHT")
+    w("44.0")
+    w("!NUMBER OF ENERGY LEVELS")
+    w(str(nlev))
+    w("!LEVEL + ENERGIES(cm^-1) + WEIGHT + J")
+    energies = []
+    for j in range(nlev):
+        x = j * (j + 1.0)
+        e = float("%.9f" % (ROTOR_B * x - ROTOR_D * x * x))
+        energies.append(e)
+        w("%5d %15.9f %6.1f %5d" % (j + 1, e, 2.0 * j + 1.0, j))
+    w("!NUMBER OF RADIATIVE TRANSITIONS")
+    w(str(nlev - 1))
+    w("!TRANS + UP + LOW + EINSTEINA(s^-1) + FREQ(GHz) + E_u(K)")
+    for j in range(1, nlev):
+        nu_cm = energies[j] - energies[j - 1]
+        nu = nu_cm * _CLIGHT
+        mu = ROTOR_MU * 1e-18
+        a = 64.0 * math.pi ** 4 * nu ** 3 * mu * mu / (3.0 * _HPLANCK * _CLIGHT ** 3) * j / (2.0 * j + 1.0)
+        w("%5d %5d %5d %11.3e %16.7f %10.2f" % (j, j + 1, j, a, nu * 1e-9, energies[j] * _HPLANCK * _CLIGHT / _KB))
+    w("!NUMBER OF COLL PARTNERS")
+    w("2")
+    for partner, label, temps, maxdj in ((1, "1 ROTOR-H2 synthetic smooth rate surface", ROTOR_TEMPS_H2, nlev),
+                                         (4, "4 ROTOR-e synthetic dipole-like rates, |dJ| <= 3", ROTOR_TEMPS_E, 3)):
+        pairs = [(ju, jl) for ju in range(1, nlev) for jl in range(ju) if ju - jl <= maxdj]
+        w("!COLLISIONS BETWEEN")
+        w(label)
+        w("!NUMBER OF COLL TRANS")
+        w(str(len(pairs)))
+        w("!NUMBER OF COLL TEMPS")
+        w(str(len(temps)))
+        w("!COLL TEMPS")
+        w(" ".join("%7.1f" % t for t in temps))
+        w("!TRANS + UP + LOW + COLLRATES(cm^3 s^-1)")
+        for k, (ju, jl) in enumerate(pairs):
+            w("%5d %5d %5d " % (k + 1, ju + 1, jl + 1) + " ".join("%10.3e" % _rotor_rate(partner, ju, jl, t) for t in temps))
+    w("!NOTES: synthetic table; collision rates are not published values")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return path
+
+
+def rotor_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "rotor21.dat")
+
+
 def default_path() -> str:
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "co.dat")
 
 
 if __name__ == "__main__":
     print(write_co_synth(default_path()))
+    print(write_rotor_synth(rotor_path()))

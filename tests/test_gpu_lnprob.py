@@ -46,6 +46,10 @@ def test_lnprob_1comp(oracle):
     assert ok.sum() > 0.7 * fin.sum()
     err = np.abs(got[ok] - ref[ok])
     assert (err < np.maximum(ATOL, 1e-9 * np.abs(ref[ok]))).all(), err.max()
+    errall = np.abs(got[fin] - ref[fin])
+    from test_gpu_solve import record
+    record("lnprob_1comp", walkers=int(P.shape[0]), finite=int(fin.sum()), well_posed=int(ok.sum()),
+           max_abs_err_well_posed=float(err.max()), finite_within_tol=int((errall < np.maximum(ATOL, 1e-9 * np.abs(ref[fin]))).sum()))
     # prior short-circuit: solves only where the prior is finite (emcee_radex.py:178-180)
     assert nsolves == np.isfinite(er1.lnprior(P, bounds)).sum()
     # scalar call form
@@ -78,6 +82,11 @@ def test_lnprob_2comp(oracle):
         assert ok.sum() > 0.6 * fin.sum()
         err = np.abs(got[ok] - ref[ok])
         assert (err < np.maximum(ATOL, 1e-9 * np.abs(ref[ok]))).all(), err.max()
+        errall = np.abs(got[fin] - ref[fin])
+        from test_gpu_solve import record
+        record("lnprob_2comp_td_%s" % td, walkers=int(P.shape[0]), finite=int(fin.sum()), well_posed=int(ok.sum()),
+               max_abs_err_well_posed=float(err.max()),
+               finite_within_tol=int((errall < np.maximum(ATOL, 1e-9 * np.abs(ref[fin]))).sum()))
         assert nsolves == 2 * np.isfinite(er2.lnprior(P, bounds, T_d=td)).sum()
     # T_d <= 0 -> -inf everywhere
     assert (er2.lnprob(P[:8], jup, flux, eflux, bounds=bounds, T_d=-1.0) == -np.inf).all()

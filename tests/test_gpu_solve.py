@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import MOLFILE, draw_params
+from oracle import parity            # the checker: classes of models, decided with the oracle alone (oracle/parity.py)
 from radex_emcee_b200 import _lib
 from radex_emcee_b200.radex import Radex
 
@@ -39,67 +40,74 @@ def gpu_solve(ctx, T, nh2, N, tbg, method=2, **optkw):
     return out
 
 
-def rel_errors(got, ref, iupp):
-    """Per-model max relative error of populations (> 1e-9), Tex/tau of those levels' lines, and
-    the fluxes of lines brighter than 1e-6 of the model's brightest."""
-    with np.errstate(all="ignore"):
-        xr = ref["xpop"]
-        sig = xr > 1e-9
-        ex = np.where(sig, np.abs(got["xpop"] - xr) / xr, 0).max(axis=1)
-        sl = sig[:, iupp - 1]
-        et = np.where(sl, np.abs(got["tex"] - ref["tex"]) / np.abs(ref["tex"]), 0)
-        eu = np.where(sl, np.abs(got["tau"] - ref["tau"]) / np.maximum(np.abs(ref["tau"]), 1e-12), 0)
-        sr = ref["surf"]
-        bright = np.abs(sr) > 1e-6 * np.nanmax(np.abs(sr), axis=1, keepdims=True)
-        bright &= np.abs(sr) > 1e-25          # erg s-1 cm-2 Hz-1 sr-1; real lines are 1e-16 .. 1e-9
-        es = np.where(bright & sl, np.abs(got["surf"] - sr) / np.abs(sr), 0)
-    f = lambda e: np.nan_to_num(e, nan=np.inf).max(axis=1)
-    return ex, f(et), f(eu), f(es)
+rel_errors = parity.rel_errors
 
 
-PERTURBATIONS = ((0, 3e-14), (1, 1e-13), (2, 1e-13), (0, -1e-12), (2, -1e-11))
+def record(name, **figures):
+    """Measured class fractions and errors of this run -> gpurun_out/parity_tests.json (copied to profiles/)."""
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if not os.path.isdir(out):
+        return
+    path = os.path.join(out, "parity_tests.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[name] = figures
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
 
 
-def well_posed(oracle, T, nh2, N, tbg, method, ref, **kw):
-    """Models on which the reference algorithm reproduces ITSELF: the oracle re-run with one input
-    perturbed in its last digits (five variants) lands on the same answer to 1e-6.  Elsewhere the
-    under-relaxed iteration wanders between attractors or ends in a limit cycle at maxiter, and
-    the reference's own output changes with the last bit of its input -- no implementation with
-    different rounding (FMA, another libm) can be asked to match it there ('ill-posed
-    models'; for the worst offenders most perturbations land on the GPU's answer, not the oracle's)."""
-    ok = np.isfinite(ref["surf"]).all(axis=1)
-    # strong masers (a line with tau < -3, amplification e^-tau) are hypersensitive by construction
-    ok &= np.nan_to_num(ref["tau"], nan=-np.inf).min(axis=1) > -3.0
-    for which, eps in PERTURBATIONS:
-        t, d, c = T.copy(), nh2.copy(), N.copy()
-        (t, d, c)[which][:] *= 1 + eps
-        pert = oracle.solve_batch(t, 0.25 * d, 0.75 * d, c, tbg=tbg, method=method, **kw)
-        ex, et, eu, es = rel_errors(pert, ref, oracle.iupp)
-        ok &= (ex < 1e-6) & (et < 1e-6) & (es < 1e-6)
-    return ok
-
-
-def compare(got, ref, ok, iupp, label=""):
+def check_against_oracle(got, T, nh2, N, tbg, method, label, min_well_posed, more=True, **kw):
+    """1e-5 on every well-posed model; on the excluded ones (the reference's own answer moves with the 13th digit of
+    its input) the GPU must land on one of the answers the reference itself gives near that input."""
+    ref, cls, runs = parity.classify(MOLFILE, T, nh2, N, tbg, method, more=more, **kw)
+    iupp = ref["iupp"]
     ex, et, eu, es = rel_errors(got, ref, iupp)
-    worst = max(ex[ok].max(), et[ok].max(), eu[ok].max(), es[ok].max())
-    assert worst < RTOL, (label, ex[ok].max(), et[ok].max(), eu[ok].max(), es[ok].max())
-    return worst
+    w = np.maximum(np.maximum(ex, et), np.maximum(eu, es))
+    wp = cls["well_posed"]
+    excl = cls["maser"] | cls["sensitive"]
+    att = parity.attractor_error(got, ref, runs, iupp)
+    nonf_agree = ((got["status"] & 8) != 0)[cls["nonfinite"]]
+    record(label, models=int(T.size), classes={k: int(v.sum()) for k, v in cls.items()},
+           well_posed_fraction=float(wp.mean()), max_err_well_posed=float(w[wp].max()),
+           max_err_pops=float(ex[wp].max()), max_err_tex=float(et[wp].max()), max_err_tau=float(eu[wp].max()),
+           max_err_flux=float(es[wp].max()), all_models_within_tol=int((w < RTOL).sum()),
+           excluded_within_tol_of_reference=int((w[excl] < RTOL).sum()),
+           excluded_within_tol_of_an_attractor=int((att[excl] < RTOL).sum()), excluded=int(excl.sum()),
+           nonfinite_flagged_by_gpu=int(nonf_agree.sum()), perturbations=len(runs))
+    assert wp.mean() >= min_well_posed, (label, wp.mean())
+    assert w[wp].max() < RTOL, (label, ex[wp].max(), et[wp].max(), eu[wp].max(), es[wp].max())
+    # excluded models of the hot path's geometry (LVG): at least four in five sit on one of the reference's own answers
+    # (a limit cycle caught at another phase need not; measured: 56/56 and 153/154 at 8192 draws).  Sphere and slab have
+    # wilder excluded classes (chaotic iterations whose state at call 200 no perturbed run repeats): recorded, not asserted.
+    # Where the reference's brightness is not finite the GPU says so too.
+    if excl.sum() >= 5 and method == 2:
+        assert (att[excl] < RTOL).mean() >= 0.8, (label, (att[excl] < RTOL).mean())
+    assert nonf_agree.all(), label
+    assert ((got["status"][wp] & 8) == 0).all()
+    return ref, cls
 
 
 @pytest.mark.parametrize("method,tbg,n", [(2, 10.926, 512), (2, 2.7315, 256), (1, 2.7315, 256), (3, 10.926, 256)])
-def test_random_sweep_vs_oracle(ctx, oracle, method, tbg, n):
+def test_random_sweep_vs_oracle(ctx, method, tbg, n):
     P = draw_params(np.random.default_rng(1000 + method + int(tbg)), n, tbg)
     T, nh2, N = P[:, 0], P[:, 1], P[:, 2]
-    ref = oracle.solve_batch(T, 0.25 * nh2, 0.75 * nh2, N, tbg=tbg, method=method)
-    ok = well_posed(oracle, T, nh2, N, tbg, method, ref)
-    assert ok.mean() > 0.7, ok.mean()
     got = gpu_solve(ctx, T, nh2, N, tbg, method)
-    compare(got, ref, ok, oracle.iupp, "sweep m%d" % method)
+    ref, cls = check_against_oracle(got, T, nh2, N, tbg, method, "sweep_method%d_tbg%.3f" % (method, tbg),
+                                    min_well_posed=0.9 if method == 2 else 0.7)
     # the iteration counter follows the reference's up to last-ULP jitter of the 1e-16 stop test
+    ok = cls["well_posed"]
     dn = np.abs(got["niter"] - ref["niter"])[ok & (ref["niter"] < 200) & (got["niter"] < 200)]
     assert np.median(dn) <= 3 and np.quantile(dn, 0.9) <= 40
-    # status bits: non-finite flag agrees with the oracle's NaNs on well-posed models
-    assert ((got["status"][ok] & 8) == 0).all()
+
+
+def test_scheduled_pipeline_vs_oracle(ctx):
+    """A batch >= 8192 models runs as the ordered launches the benchmark times (A, counting sort, B, k_lvg_small<3..7>,
+    C): the same 1e-5 bar against the oracle, on config-2 draws (the oracle side runs on all host cores)."""
+    P = draw_params(np.random.default_rng(1), 8192, 10.926)
+    T, nh2, N = P[:, 0], P[:, 1], P[:, 2]
+    got = gpu_solve(ctx, T, nh2, N, 10.926)
+    assert ctx.cache_stats()[1] > 7000          # the captures were made: this was the scheduled path
+    check_against_oracle(got, T, nh2, N, 10.926, 2, "scheduled_pipeline_8192", min_well_posed=0.9)
 
 
 def test_vs_reference_binary_fixtures(ctx, oracle, golden_solve):
@@ -120,16 +128,36 @@ def test_vs_reference_binary_fixtures(ctx, oracle, golden_solve):
             assert (np.abs(got["tex"][both] - ref["tex"][both]) / np.abs(ref["tex"][both]))[sl].max() < RTOL
 
 
-def test_radex_native_stop_rule(ctx, oracle):
+def test_radex_native_stop_rule(ctx):
+    """RADEX's own conv flag stops at an UNCONVERGED state, so the comparison is made state by state: the GPU is run
+    for exactly as many matrix() calls as the oracle made (no stop test on the GPU side: abs_tol = 0, maxiter = that
+    count) and must hold the oracle's populations, Tex and tau to 1e-5; separately, the GPU's own evaluation of the rule
+    must stop at the same call on (nearly) every well-posed model -- counted, not used as a filter."""
     from oracle.oracle import STOP_RADEX
     P = draw_params(np.random.default_rng(5), 256, 10.926)
     T, nh2, N = P[:, 0], P[:, 1], P[:, 2]
-    ref = oracle.solve_batch(T, 0.25 * nh2, 0.75 * nh2, N, tbg=10.926, stop_rule=STOP_RADEX)
-    ok = well_posed(oracle, T, nh2, N, 10.926, 2, ref, stop_rule=STOP_RADEX)
-    got = gpu_solve(ctx, T, nh2, N, 10.926, stop_rule=_lib.STOP_RADEX)
-    ok &= got["niter"] == ref["niter"]      # same number of matrix() calls -> same (unconverged) state
-    assert ok.mean() > 0.7
-    compare(got, ref, ok, oracle.iupp, "radex rule")
+    ref, cls, runs = parity.classify(MOLFILE, T, nh2, N, 10.926, stop_rule=STOP_RADEX)
+    wp = cls["well_posed"]
+    assert wp.mean() > 0.9
+    forced = None
+    for k in np.unique(ref["niter"]):
+        m = ref["niter"] == k
+        calls = int(k) if k >= 200 else int(k) + 1        # the loop makes niter + 1 calls unless it ran into the cap
+        part = gpu_solve(ctx, T[m], nh2[m], N[m], 10.926, maxiter=calls, abs_tol=0.0)
+        assert (part["niter"] == calls).all() and (part["status"] & 4).all()
+        if forced is None:
+            forced = {key: np.empty((T.size,) + v.shape[1:], v.dtype) for key, v in part.items()}
+        for key in forced:
+            forced[key][m] = part[key]
+    wf = parity.worst(forced, ref, ref["iupp"])
+    assert wf[wp].max() < RTOL, wf[wp].max()
+    own = gpu_solve(ctx, T, nh2, N, 10.926, stop_rule=_lib.STOP_RADEX)
+    same = own["niter"] == ref["niter"]
+    wo = parity.worst(own, ref, ref["iupp"])
+    record("radex_rule", models=256, well_posed=int(wp.sum()), state_at_reference_call_count_max_err=float(wf[wp].max()),
+           own_stop_same_call=int(same[wp].sum()), own_stop_max_err=float(wo[wp & same].max()))
+    assert same[wp].mean() >= 0.95, same[wp].mean()
+    assert wo[wp & same].max() < RTOL
 
 
 def test_edge_cases(ctx, oracle):
