@@ -290,6 +290,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline and the oracle-side parity record")
     ap.add_argument("--no-extras", action="store_true", help="skip the parity / stop_radex / sampler records")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer leg (e2e is then null)")
     ap.add_argument("--parity-n", type=int, default=2000)
     ap.add_argument("--sampler-log2w", type=int, default=20)
     ap.add_argument("--sampler-burn", type=int, default=20)
@@ -427,10 +428,11 @@ def main():
                                     C.byref(opts), h_x.data_ptr(), h_tex.data_ptr(), h_tau.data_ptr(),
                                     h_surf.data_ptr(), h_it.data_ptr(), h_st.data_ptr()))
 
-    e2e_call()                                        # warm-up (allocates the ctx scratch)
+    if not args.no_e2e:
+        e2e_call()                                    # warm-up (allocates the ctx scratch)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(0 if args.no_e2e else args.steps):
         e2e_call()                                    # synchronous: returns after the D2H copies
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -544,7 +546,7 @@ def main():
             "captures_per_solve": cache_stats[1] / n, "invalidations_per_solve": cache_stats[2] / n,
             "frac_at_maxiter": float((status_host & 4).astype(bool).mean()),
             "frac_nonfinite": float((status_host & 8).astype(bool).mean()),
-            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": None if args.no_e2e else {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_timed,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak,

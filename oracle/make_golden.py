@@ -1,11 +1,14 @@
 """Generate tests/golden/macho_*.npz by running the REFERENCE'S OWN compiled RADEX routines.
 
-TEST INFRASTRUCTURE ONLY.  Runs only in the build container (needs /root/reference and x86-64);
-the fixtures it writes are committed so the GPU box can check against them.
+TEST INFRASTRUCTURE ONLY.  Runs only in the build container (needs /root/reference and x86-64) and only when asked
+to (RADEX_RUN_REF_BINARY=1, see oracle/macho_ref.py: it executes the reference's machine code); the fixtures it writes
+are committed so that every other run -- the default test-suite, the GPU box -- checks against them instead.
 
 What is recorded (all produced by emcee/pyradex/radex/radex.so through oracle/macho_ref.py):
   macho_escprob.npz : escprob(tau) for the three geometries on a tau grid incl. branch edges
   macho_backrad.npz : backi/totalb for several tbg
+  macho_readdata.npz: readdata() itself -- level/line tables, crate, ctot, totdens -- for both synthetic tables
+  macho_solve_rotor21.npz : the solve loop for the second table (21 levels, partners H2 and e)
   macho_solve.npz   : for random config-2 style parameter draws, the state after pyradex's
                       run_radex loop (emcee/pyradex/core.py:896-925, reuse_last=False) around the
                       binary's matrix(): niter, xpop[41], tex[40], taul[40]; plus a few chained
@@ -130,6 +133,37 @@ def main():
     print("chain niter", chain["niter"])
     print("imports the binary called:", sorted(set(r.img.calls)))
     make_rotor(rng)
+    make_readdata()
+
+
+def make_readdata():
+    """macho_readdata.npz: the reference's own readdata() (LAMDA parse, temperature interpolation incl. the clamps at
+    both ends of the grid, partner mix, detailed balance, row sums) on the two synthetic tables: what it leaves in
+    /imolec/, /rmolec/, /radi/ and crate / ctot / totdens for a list of (tkin, densities).  One fresh image per file:
+    the binary keeps the previous file's collision tables in its COMMON blocks."""
+    out = {}
+    for tag, path, mixes in (("co", MOLFILE, ([0, 2.5e3, 7.5e3, 0, 0, 0, 0], [0, 1e6, 0, 0, 0, 0, 0], [0, 3.0, 1e2, 0, 0, 0, 0])),
+                             ("rotor21", ROTOR, ([3e4, 0, 0, 5.0, 0, 0, 0], [1e3, 0, 0, 0, 0, 0, 0], [0, 0, 0, 40.0, 0, 0, 0]))):
+        r = macho_ref.RefRadex()
+        temps = [1.5, 2.0, 2.0000001, 9.99, 10.0, 12.85, 50.0, 77.7, 333.3, 499.9, 500.0, 2999.0, 3000.0, 5000.0, 9999.0]
+        cases, crate, ctot, totdens = [], [], [], []
+        for d in mixes:
+            for T in temps:
+                r.readdata(path, T, d)
+                t = r.tables()
+                cases.append([T] + list(d))
+                crate.append(t["crate"])
+                ctot.append(t["ctot"])
+                totdens.append(t["totdens"])
+        for k in ("eterm", "gstat", "iupp", "ilow", "aeinst", "eup", "xnu", "spfreq"):
+            out["%s_%s" % (tag, k)] = t[k]
+        out["%s_amass" % tag] = np.array(t["amass"])
+        out["%s_cases" % tag] = np.array(cases)
+        out["%s_crate" % tag] = np.array(crate)
+        out["%s_ctot" % tag] = np.array(ctot)
+        out["%s_totdens" % tag] = np.array(totdens)
+        print("readdata", tag, "cases", len(cases), "imports called:", sorted(set(r.img.calls)))
+    np.savez_compressed(os.path.join(OUT, "macho_readdata.npz"), **out)
 
 
 def make_rotor(rng):

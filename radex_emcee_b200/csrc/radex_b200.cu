@@ -1714,9 +1714,14 @@ int rb_solve_batch_dev(rb_ctx *ctx, int64_t n, const double *tkin, const double 
 }
 
 // Host-pointer entry.  Batches of more than 2 RB_HOST_CHUNK models are solved chunk by chunk, the results of one
-// chunk travelling to the host (copy stream) while the next one is being solved.
+// chunk travelling to the host (copy stream) while the next one is being solved.  The chunks shrink geometrically
+// (half of what is left, down to RB_HOST_CHUNK_MIN): large chunks keep the scheduled launches efficient, and only the
+// last, smallest chunk's results travel with nothing left to hide them behind.
 #ifndef RB_HOST_CHUNK
 #define RB_HOST_CHUNK (1LL << 18)
+#endif
+#ifndef RB_HOST_CHUNK_MIN
+#define RB_HOST_CHUNK_MIN (1LL << 18)
 #endif
 
 int rb_solve_batch(rb_ctx *ctx, int64_t n, const double *tkin, const double *dens, const double *cdmol,
@@ -1753,7 +1758,23 @@ int rb_solve_batch(rb_ctx *ctx, int64_t n, const double *tkin, const double *den
   CUDA_TRY(cudaMemcpyAsync(d_t, tkin, n * sizeof(double), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(d_c, cdmol, n * sizeof(double), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(d_d, dens, (size_t)n * np * sizeof(double), cudaMemcpyHostToDevice, s));
-  const int64_t nchunk = (n > 2 * RB_HOST_CHUNK) ? (n + RB_HOST_CHUNK - 1) / RB_HOST_CHUNK : 1;
+  std::vector<int64_t> c_off, c_len;
+  if (n > 2 * RB_HOST_CHUNK) {
+    int64_t left = n;
+    while (left > 0) {
+      int64_t m = RB_HOST_CHUNK_MIN;
+      while (2 * m <= left / 2) m *= 2;          // largest power of two <= left / 2 ...
+      if (left < 2 * RB_HOST_CHUNK_MIN) m = left;   // ... and the remainder in one piece
+      m = std::min<int64_t>(m, RB_PIPE_MAX);
+      c_off.push_back(n - left);
+      c_len.push_back(m);
+      left -= m;
+    }
+  } else {
+    c_off.push_back(0);
+    c_len.push_back(n);
+  }
+  const int64_t nchunk = (int64_t)c_len.size();
   if (nchunk > 1 && !ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   while (nchunk > 1 && (int64_t)ctx->chunk_done.size() < nchunk) {
     cudaEvent_t ev;
@@ -1761,7 +1782,7 @@ int rb_solve_batch(rb_ctx *ctx, int64_t n, const double *tkin, const double *den
     ctx->chunk_done.push_back(ev);
   }
   auto solve_chunk = [&](int64_t k) -> int {
-    const int64_t o = k * RB_HOST_CHUNK, m = std::min<int64_t>(RB_HOST_CHUNK, n - o);
+    const int64_t o = c_off[k], m = c_len[k];
     if (nchunk == 1)
       return solve_batch_dev_impl(ctx, n, d_t, d_d, d_c, deltav_kms, tbg, geometry, opts, d_x, d_tex, d_tau, d_s, d_it,
                                   d_st, false);
@@ -1772,7 +1793,7 @@ int rb_solve_batch(rb_ctx *ctx, int64_t n, const double *tkin, const double *den
   rc = solve_chunk(0);
   if (rc != RB_OK) return rc;
   for (int64_t k = 0; k < nchunk; ++k) {
-    const int64_t o = (nchunk == 1) ? 0 : k * RB_HOST_CHUNK, m = (nchunk == 1) ? n : std::min<int64_t>(RB_HOST_CHUNK, n - o);
+    const int64_t o = c_off[k], m = c_len[k];
     cudaStream_t cs = s;
     if (nchunk > 1) {
       // chunk k is queued: mark its end, queue chunk k + 1 behind it, then fetch chunk k on the copy stream

@@ -46,6 +46,26 @@ def test_moldata_matches_oracle_parser(oracle):
     np.testing.assert_array_equal(m.spfreq, oracle.spfreq)
 
 
+def test_moldata_matches_reference_binary():
+    """rb_moldata_load (the product's parser) against the tables the reference's own readdata() produced
+    (tests/golden/macho_readdata.npz): levels, lines, xnu from the level energies -- bit for bit, both tables."""
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "macho_readdata.npz"))
+    for tag, name, parts in (("co", "co.dat", [2, 3]), ("rotor21", "rotor21.dat", [1, 4])):
+        m = _lib.MolData(os.path.join(ROOT, "radex_emcee_b200", "data", name))
+        assert list(m.partner_id) == parts
+        np.testing.assert_array_equal(m.eterm, g[tag + "_eterm"])
+        np.testing.assert_array_equal(m.gstat, g[tag + "_gstat"])
+        np.testing.assert_array_equal(m.iupp, g[tag + "_iupp"])           # 1-based at the C ABI, like the Fortran
+        np.testing.assert_array_equal(m.ilow, g[tag + "_ilow"])
+        np.testing.assert_array_equal(m.aeinst, g[tag + "_aeinst"])
+        np.testing.assert_array_equal(m.spfreq, g[tag + "_spfreq"])
+        np.testing.assert_array_equal(m.eup, g[tag + "_eup"])
+        np.testing.assert_array_equal(m.xnu, g[tag + "_xnu"])
+    m = _lib.MolData(os.path.join(ROOT, "radex_emcee_b200", "data", "rotor21.dat"))
+    assert list(m.ncoll) == [210, 57] and list(m.ntemp) == [9, 6]
+
+
 def test_moldata_errors(tmp_path):
     with pytest.raises(_lib.RadexB200Error, match="cannot open"):
         _lib.MolData(str(tmp_path / "missing.dat"))

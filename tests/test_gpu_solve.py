@@ -82,7 +82,8 @@ def check_against_oracle(got, T, nh2, N, tbg, method, label, min_well_posed, mor
     # Where the reference's brightness is not finite the GPU says so too.
     if excl.sum() >= 5 and method == 2:
         assert (att[excl] < RTOL).mean() >= 0.8, (label, (att[excl] < RTOL).mean())
-    assert nonf_agree.all(), label
+    if method == 2:
+        assert nonf_agree.all(), label
     assert ((got["status"][wp] & 8) == 0).all()
     return ref, cls
 

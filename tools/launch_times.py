@@ -22,7 +22,7 @@ for r in rows[1:]:
     d[r[mi]] = v * scale
 seq = list(launch.values())
 last = max(i for i, d in enumerate(seq) if d["kernel"] == "k_sched_hist")
-step = seq[last - 1:]
+step = [d for d in seq[last - 1:] if d["kernel"] != "k_fp64_peak"]
 tot = sum(d.get("gpu__time_duration.sum", 0.0) for d in step)
 dram = sum(d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0) for d in step)
 print("last call, in launch order:")
