@@ -10,7 +10,7 @@
 // and for n <= 16 two models share a warp (lanes 0-15 / 16-31, each half with its own slab, iteration state and
 // queue ticket): 32 / 26 / 20 / 17 / 15 models per SM for 12 / 16 / 20 / 24 / 28 lead levels.
 // There is NO full elimination in these kernels: launch A (v2::solve, sched = 1) captures the frozen top of a model
-// and parks lead block, response matrix and line bases (EXT_STRIDE doubles); a model whose frozen lines turn thick is
+// and parks lead block, response matrix and line bases (v2::ext_size(n) doubles); a model whose frozen lines turn thick is
 // parked again and finished by launch C (v2::solve, sched = 4).
 //
 // Per model the arithmetic is the one of v2::lead_solve and of the iteration loop of v2::solve, operation for
@@ -41,7 +41,6 @@ using v2::st2;
 
 using v2::KP_SMALL_MAX;               // largest lead block (in panels) with an engine here
 using v2::EXT_LEAD;
-using v2::EXT_STRIDE;
 // ---- per-model shared-memory slab (doubles), for a lead block of N = 4 KP levels -------------------------
 // KP = 3: 870 doubles (6960 B, 32 models = 16 warps per SM); KP = 4: 1100 doubles (8800 B, 26 models = 13 warps)
 template <int KP>
@@ -67,7 +66,7 @@ struct Lay {
 };
 // ---- per-CTA constants (the same for every model of a call) --------------------------------------------
 constexpr int C_LA = 0, C_LGR = 40, C_LTDEN = 80, C_LECOEF = 120, C_LFKXNU = 160, C_LMN = 200, CSLAB = 220;
-// parked capture (global, per model; v2::EXT_STRIDE = 784 doubles): DNB[40] UPB[40] lead[n(n+2)] M[n(42-n)]
+// parked capture (global, per model; v2::ext_size(n) doubles at io.ext + io.ext_off[model]): DNB[40] UPB[40] lead[n(n+2)] M[n(42-n)]
 template <int KP>
 constexpr size_t smem_bytes() { return (size_t)(CSLAB + Lay<KP>::MPW * Lay<KP>::WARPS * Lay<KP>::SSLAB) * sizeof(double); }
 static_assert(smem_bytes<3>() <= 232448 && smem_bytes<4>() <= 232448 && smem_bytes<5>() <= 232448 &&

@@ -506,7 +506,9 @@ struct SolveIO {
   double *obs_surf;
   int nobs;
   int obs_line[RB_MAX_OBS];
-  double *ext;                         // n x v2s::EXT_STRIDE
+  double *ext;                         // parked captures: v2::ext_size(n) doubles per cacheable model, at ext + ext_off[model]
+  long long *ext_off;
+  long long ext_cap;                   // doubles in ext
   unsigned long long *sched_small;     // [16+k] first queue position of key k, [48] parked, [49] models for launch C
   int *order_c;
   int queue;                           // work-queue head of this launch: counters[queue] (0, or 8.. when launches overlap)
@@ -715,9 +717,10 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
     for (int p = 0; p < RB_MAXPART; ++p) dens[p] = (p < mol.npart) ? io.dens[idx * mol.npart + p] : 0.0;
     int st = 0, key = -1;
     const double cdmol = io.cdmol[idx];
+    const v2::ExtPark xp{io.ext, io.sched_small ? io.sched_small + 50 : nullptr, io.ext_cap, io.ext_off};
     const int it = v2::solve(mol, sm, gB, phase, lane, io.tkin[idx], dens, cdmol, cfg.tbg, cfg, &st, io.sched,
                              io.state ? io.state + idx * v2::STATE_STRIDE : nullptr, &key,
-                             (io.sched == 1 && io.ext) ? io.ext + idx * v2::EXT_STRIDE : nullptr);
+                             (io.sched == 1 && io.ext) ? &xp : nullptr, (long long)idx);
     if (io.sched == 1 && lane == 0) io.keys[idx] = (st & v2::ST_PARKED) ? key : -1;
     if (st & v2::ST_PARKED) {   // launch B finishes this model
       iters += (unsigned long long)it;
@@ -853,7 +856,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     if (need_load) {
       need_load = false;
       const double *st = io.state + idx * v2::STATE_STRIDE;
-      const double *ex = io.ext + idx * EXT_STRIDE;
+      const double *ex = io.ext + io.ext_off[idx];
       for (int i = hl; i < NL; i += G) sm[S_X + i] = st[i];
       const unsigned long long bits = reinterpret_cast<const unsigned long long *>(st)[121];
       const long long packed = reinterpret_cast<const long long *>(st)[122];
@@ -1483,28 +1486,26 @@ int rb_ctx_create(int device, const rb_mol *mol, rb_ctx **out) {
     rc = RB_ERR_CUDA;
   }
   if (rc == RB_OK) {
-    const Launch L = v1_launch(ctx, 1 << 20);
-    cudaError_t e = cudaFuncSetAttribute(k_lvg_solve_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-    if (mol->nlev == v2::NL && mol->nline <= v2::MAXLINE) {
-      const int sm2 = (int)(V2_WARPS * v2::SLAB * sizeof(double));
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_solve_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_lvg_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<3>());
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_lvg_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<4>());
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_lvg_small<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<5>());
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_lvg_small<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<6>());
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_lvg_small<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem<7>());
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm2);
-      if (e == cudaSuccess)
-        e = cudaMalloc(&ctx->bslab, (size_t)ctx->sm_count * V2_WARPS * v2::GSLAB * sizeof(double));
+    // every kernel may use the whole opt-in shared memory of the device: the attribute belongs to the function, not to
+    // the context, so it must not depend on which molecule this context holds
+    const int smax = ctx->smem_optin;
+    cudaError_t e = cudaFuncSetAttribute(k_lvg_solve_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_solve_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_small<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_small<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvg_small<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lnprob_v2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+    if (e == cudaSuccess && (size_t)smax < (size_t)V2_WARPS * v2::SLAB * sizeof(double)) {
+      rb_set_error("device offers less shared memory per block than the kernels need");
+      rc = RB_ERR_LIMIT;
     }
+    if (e == cudaSuccess && rc == RB_OK && mol->nlev == v2::NL && mol->nline <= v2::MAXLINE)
+      e = cudaMalloc(&ctx->bslab, (size_t)ctx->sm_count * V2_WARPS * v2::GSLAB * sizeof(double));
     if (e != cudaSuccess) {
       rb_set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
       rc = RB_ERR_CUDA;
@@ -1566,7 +1567,7 @@ int rb_ctx_reset_stream(rb_ctx *ctx) {
 #define RB_MID_MIN (1LL << 17)   // batches from this size on also run the 20/24/28-level lead blocks in their own launches
                                  // (measured with the launches overlapping: 2^16 models 4 % slower with the three extra
                                  // launches, 2^17 2 % faster, 2^20 6 % faster)
-#define RB_PIPE_MAX (1LL << 20)   // models per scheduled pass: bounds the parked captures at 12.5 GB
+#define RB_PIPE_MAX (1LL << 20)   // models per scheduled pass: bounds the parked state + captures at 1 + 7 GB
 
 static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg_in, SolveIO io, const Launch &L) {
   if (io.n > RB_PIPE_MAX && cfg_in.small) {   // larger batches: one pass per 2^20 models, totals keep accumulating
@@ -1593,10 +1594,12 @@ static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg_in, SolveIO io
   const long long n = io.n;
   SolveCfg cfg = cfg_in;
   if (cfg.park_max == 0) cfg.park_max = (n >= RB_MID_MIN) ? v2::KP_SMALL_MAX : 4;
-  const bool small = cfg.small != 0;   // the parked captures take 10.9 KB per model
+  const bool small = cfg.small != 0;   // the parked captures take 4.9 .. 10.5 KB per cacheable model, EXT_AVG x 8 B budgeted
   const size_t b_state = align256((size_t)n * v2::STATE_STRIDE * sizeof(double)), b_int = align256((size_t)n * sizeof(int));
-  const size_t b_ext = small ? align256((size_t)n * v2::EXT_STRIDE * sizeof(double)) : 0;
-  const size_t b_all = b_state + (small ? 3 : 2) * b_int + b_ext;
+  const long long ext_cap = (long long)n * v2::EXT_AVG;
+  const size_t b_off = small ? align256((size_t)n * sizeof(long long)) : 0;
+  const size_t b_ext = small ? align256((size_t)ext_cap * sizeof(double)) : 0;
+  const size_t b_all = b_state + (small ? 3 : 2) * b_int + b_off + b_ext;
   if (b_all > ctx->sched_bytes) {
     if (ctx->sched_buf) cudaFree(ctx->sched_buf);
     ctx->sched_buf = nullptr;
@@ -1612,7 +1615,9 @@ static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg_in, SolveIO io
   io.sched_small = ctx->sched_small;
   if (small) {
     io.order_c = reinterpret_cast<int *>(base + b_state + 2 * b_int);
-    io.ext = reinterpret_cast<double *>(base + b_state + 3 * b_int);
+    io.ext_off = reinterpret_cast<long long *>(base + b_state + 3 * b_int);
+    io.ext = reinterpret_cast<double *>(base + b_state + 3 * b_int + b_off);
+    io.ext_cap = ext_cap;
   }
   CUDA_TRY(cudaMemsetAsync(ctx->sched_small, 0, 64 * sizeof(unsigned long long), ctx->stream));
   io.sched = 1;

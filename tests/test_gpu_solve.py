@@ -296,6 +296,27 @@ def test_ordered_launches_without_half_warp_engine_are_bit_identical(ctx):
                 np.testing.assert_array_equal(a[k], ref[k], err_msg="%s %s kernel %d park_max %s" % (k, kw, kernel, park_max))
 
 
+def test_capture_buffer_overflow_finishes_in_launch_a(ctx):
+    """Launch A parks every capture in one buffer budgeted at 832 doubles per model of the batch; a batch made only of
+    models with the largest cacheable lead block (28 levels: 1312 doubles each) cannot fit.  The models that find the
+    buffer full finish inside launch A (the single-launch path): same numbers as kernel=3, bit for bit."""
+    P = draw_params(np.random.default_rng(91), 30000, 10.926)
+    first = gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 10.926, kernel=3)
+    thick = ~(np.abs(first["tau"]) * 0.5 < np.float32(0.01))
+    top = np.where(thick.any(axis=1), thick.shape[1] - np.argmax(thick[:, ::-1], axis=1), -1)
+    sel = np.nonzero(np.maximum(3, (top + 1 + 4) >> 2) == 7)[0]
+    assert sel.size > 300
+    Q = P[np.resize(sel, 12000)]
+    Q[:, 0] *= 1.0 + 1e-9 * np.arange(12000)        # distinct models of the same class
+    a = gpu_solve(ctx, Q[:, 0], Q[:, 1], Q[:, 2], 10.926, park_max=7)
+    ita, _ = ctx.counters()
+    b = gpu_solve(ctx, Q[:, 0], Q[:, 1], Q[:, 2], 10.926, kernel=3)
+    itb, _ = ctx.counters()
+    assert ita == itb
+    for k in ("xpop", "tex", "tau", "surf", "niter", "status"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
 def test_chunked_host_entry(ctx):
     """rb_solve_batch with host buffers solves batches of more than 2 x 2^18 models chunk by chunk, copying one
     chunk's results back while the next is solved: same numbers as direct calls on slices, totals accumulated."""
