@@ -296,6 +296,7 @@ def main():
     ap.add_argument("--sampler-burn", type=int, default=20)
     ap.add_argument("--sampler-steps", type=int, default=10)
     ap.add_argument("--keep", default="", help="debug: small | big | k57 | k8 -- keep only the models whose lead block (from a first pass) has <= 16 | > 16 | 20..28 | > 28 levels, tiled to n")
+    ap.add_argument("--park-max", type=int, default=0, help="rb_opts.park_max (profiling aid: 7 gives the 20/24/28-level engines their own launches on small batches)")
     ap.add_argument("--kernel", type=int, default=0, help="rb_opts.kernel: 0 default, 1 v1 LU, 2 v2 without caching, 3 single launch, 4 without the half-warp engine")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -358,7 +359,7 @@ def main():
     d_it = torch.empty(n, dtype=torch.int32, device=dev)
     d_st = torch.empty(n, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    opts = _lib.default_opts(stop_rule=stop_rule, kernel=args.kernel, abs_tol=args.abs_tol)
+    opts = _lib.default_opts(stop_rule=stop_rule, kernel=args.kernel, abs_tol=args.abs_tol, park_max=args.park_max)
     stream = torch.cuda.current_stream(dev)
     ctx.set_stream(stream.cuda_stream)
 

@@ -85,18 +85,9 @@ __device__ __forceinline__ double group_sum(double v) {   // butterfly over the 
   for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-template <int G>
-__device__ __forceinline__ int group_sum_int(int v) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-template <int G>
-__device__ __forceinline__ int group_max_int(int v) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
+// integer reductions over the lanes of a model: one REDUX instruction on the model's lane mask
+__device__ __forceinline__ int group_sum_int(unsigned mask, int v) { return __reduce_add_sync(mask, v); }
+__device__ __forceinline__ int group_max_int(unsigned mask, int v) { return __reduce_max_sync(mask, v); }
 
 template <int LO, int HI, int NR>
 __device__ __forceinline__ double sum_range(const double (&q)[NR]) {   // same association as v2::sum_range

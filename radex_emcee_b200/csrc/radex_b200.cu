@@ -952,11 +952,11 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
       }
     }
     flags = nflags;
-    topthick = group_max_int<G>(topthick);
+    topthick = group_max_int(hmask, topthick);
     bool stop;
     if (cfg.stop_rule == RB_STOP_RADEX) {
       int conv = 0;
-      nthick = group_sum_int<G>(nthick);
+      nthick = group_sum_int(hmask, nthick);
       const double tsum = (G == 16) ? group_sum<G>(tsA + tsB) : group_sum<G>(tsA);
       if (it >= 10) {
         if (nthick_this == 0) conv = 1;
