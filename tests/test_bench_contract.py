@@ -15,8 +15,31 @@ def _latest(pattern):
     return json.load(open(files[-1]))
 
 
+def test_round2_line_carries_parity_sampler_and_stop_rule_records():
+    """BASELINE.json's metric is 'LVG solves/s & walker-steps/s ...; flux rel-err': the line the driver records holds all
+    three, at one GPU and at several (the sampler record exercises the NCCL all-gather there)."""
+    for pattern in ("r2*_bench_n1.json", "r2*_bench_n2.json"):
+        d = _latest(pattern)
+        assert BASE | {"roofline", "gpu_launches", "clocks", "parity", "sampler", "stop_radex"} <= set(d), pattern
+        p = d["parity"]
+        assert p["models"] >= 2000 and p["tolerance"] == 1e-5
+        assert p["well_posed"]["within_tolerance"] == p["classes"]["well_posed"] > 0.9 * p["models"]
+        assert p["well_posed"]["max_rel_err_flux"] < 1e-5 and p["well_posed"]["max_rel_err_pops"] < 1e-5
+        assert sum(p["classes"].values()) == p["models"]
+        s = d["sampler"]
+        assert s["walkers"] == 1 << 20 and s["steps"] >= 10 and s["burn_steps"] >= 10
+        assert s["walker_steps_per_s"] > 0 and s["solves_per_s"] > s["walker_steps_per_s"]
+        assert 0 <= s["allgather"]["fraction"] < 0.5
+        if d["n_gpus"] > 1:
+            assert "NCCL" in s["allgather"]["collective"] and s["allgather"]["fraction"] > 0
+        r = d["stop_radex"]
+        assert r["value"] > d["value"] and r["iters_per_solve"] < d["iters_per_solve"]
+        assert len(r["error_vs_fixed_point"]["flux_rel_err"]) == 5
+        assert d["roofline"]["traffic"] is None or d["roofline"]["traffic"] > d["e2e"]["d2h_bytes_per_step"]
+
+
 def test_own_arm_line():
-    d = _latest("r1*_bench_n1.json")
+    d = _latest("r*_bench_n1.json")
     assert BASE | {"roofline", "cpu_baseline", "gpu_launches", "clocks"} <= set(d)
     assert d["metric"] == "LVG solves/s" and d["unit"] == "solves/s" and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
@@ -35,7 +58,7 @@ def test_own_arm_line():
 
 
 def test_reference_arm_line():
-    d = _latest("r1*_bench_reference.json")
+    d = _latest("r*_bench_reference.json")
     assert BASE | {"impl", "cpu_baseline"} <= set(d)
     assert d["impl"] == "reference" and d["metric"] == "LVG solves/s" and d["unit"] == "solves/s"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
