@@ -234,6 +234,78 @@ def fit_source(source, data, ncomp=1, nwalkers=None, n_iter_burn=100, n_iter_wal
     return result
 
 
+def fit_sources_concurrently(sources, data, ncomp=1, nwalkers=None, n_iter_burn=100, n_iter_walk=None, seed=20170914,
+                             device=0, datapath=None, opts=None, outdir=None, allow_synthetic=False):
+    """BASELINE.json configs[3]: every source of the table in ONE ensemble.  The reference fits the sources one after the
+    other (emcee_radex.py:389); here the pre-fits run per source (they are a few dozen batched launches each) and the
+    walkers of all sources -- each with its own background temperature, bounds, line set and, with two components, dust
+    temperature -- step together: ``nwalkers`` per source, partners drawn inside the source's own sub-ensemble, one fused
+    lnprob launch per half-step for all of them.  Under torchrun the ensemble is sharded over the ranks (whole sources per
+    rank).  Returns one result dict per source, the same items ``fit_source`` returns."""
+    from .radex import Radex
+    from .sampler import CudaEngine, SLEDModel, StretchSampler
+
+    mod = _modules(ncomp)
+    if nwalkers is None:
+        nwalkers = 100 if ncomp == 1 else 400
+    if n_iter_walk is None:
+        n_iter_walk = 500 if ncomp == 1 else 1000
+    ndim = 4 * ncomp
+    setups, models, starts = [], [], []
+    R = None
+    for k, source in enumerate(sources):
+        if ncomp == 1:
+            z, line_width, Jup, flux, eflux = get_source(source, data)
+            T_d = None
+        else:
+            z, T_d, line_width, Jup, flux, eflux = get_source(source, data)
+        tbg, _ra, bounds, p0 = mod.source_setup(z)
+        if R is None:
+            R = Radex(species="co", datapath=datapath, density={"oH2": mod.fortho * 1e10, "pH2": (1 - mod.fortho) * 1e10},
+                      column=1e6, temperature=20.0, tbackground=tbg, deltav=1.0, escapeProbGeom="lvg", device=device)
+            if R.molfile_is_synthetic and not allow_synthetic:
+                raise ValueError("%s is the synthetic CO-like table shipped for tests: pass datapath= / --datapath, or "
+                                 "allow_synthetic=True (--allow-synthetic)" % R.molpath)
+        R.set_params(tbg=tbg)
+        popt, pcov, pmin, info = prefit(ncomp, R, Jup, flux, eflux, bounds, p0, T_d=T_d, opts=opts)
+        rng = np.random.RandomState(seed + k)
+        starts.append(np.array([popt + 1e-3 * rng.randn(ndim) for _ in range(nwalkers)]))
+        models.append(SLEDModel(ncomp, Jup, flux, eflux, bounds, tbg, T_d=T_d, opts=opts))
+        setups.append(dict(source=source, z=z, bounds=bounds, T_d=T_d, data=(Jup, flux, eflux), popt=popt, pcov=pcov,
+                           pmin=pmin, prefit_info=info))
+    eng = CudaEngine(R._ctx, models)
+    sampler = StretchSampler(nwalkers * len(sources), ndim, eng, seed=seed, nsources=len(sources))
+    logger.info("burning samples (%d sources x %d walkers in one ensemble)", len(sources), nwalkers)
+    sampler.run_mcmc(np.vstack(starts), n_iter_burn, store=False)
+    sampler.reset()
+    logger.info("walking")
+    sampler.run_mcmc(None, n_iter_walk)
+    chain, lnp, acc = sampler.get_chain(), sampler.get_log_prob(), sampler.acceptance_fraction
+    results = []
+    for k, st in enumerate(setups):
+        sl = slice(k * nwalkers, (k + 1) * nwalkers)
+        c, l = np.ascontiguousarray(chain[:, sl]), np.ascontiguousarray(lnp[:, sl])
+        flat = c.reshape(-1, ndim)
+        res = dict(st, theta_med=np.percentile(flat, 50, axis=0), chain=c, lnprobability=l,
+                   summary=posterior_summary(flat, ncomp), acceptance_fraction=float(np.mean(acc[sl])),
+                   acceptance_fraction_per_walker=acc[sl], molfile=R.molpath, molfile_synthetic=R.molfile_is_synthetic)
+        if outdir is not None and sampler.rank == 0:
+            os.makedirs(outdir, exist_ok=True)
+            if ncomp == 1:
+                name = os.path.join(outdir, "%s_bounds.pickle" % st["source"])
+                payload = (st["source"], st["z"], st["bounds"], st["data"], (st["popt"], st["pcov"]), st["pmin"],
+                           res["theta_med"], (c, l))
+            else:
+                name = os.path.join(outdir, "%s_bounds_2comp.pickle" % st["source"])
+                payload = (st["source"], st["z"], st["bounds"], st["T_d"], st["data"], (st["popt"], st["pcov"]), st["pmin"],
+                           res["theta_med"], (c, l))
+            with open(name, "wb") as f:
+                pickle.dump(payload, f)
+            res["pickle"] = name
+        results.append(res)
+    return results
+
+
 def print_summary(res, ncomp, file=None):
     """The 'xxx:' block of the reference (emcee_radex.py:520-531, emcee_radex_2comp.py:599-608)."""
     out = file or sys.stdout
@@ -262,6 +334,8 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=20170914)
     ap.add_argument("--datapath", default=None, help="directory holding the LAMDA co.dat (the reference's radex_moldata/); "
                                                      "default: $RADEX_DATAPATH")
+    ap.add_argument("--concurrent", action="store_true",
+                    help="all sources in one ensemble (BASELINE configs[3]); with torchrun the ensemble is sharded over the ranks")
     ap.add_argument("--allow-synthetic", action="store_true",
                     help="fit with the synthetic test table shipped in the package (NOT physical)")
     args = ap.parse_args(argv)
@@ -273,6 +347,20 @@ def main(argv=None):
     outdir = args.out or ("./single" if args.ncomp == 1 else "./double")
     data = read_data(datafile)
     sources = [s for s in data if args.sources is None or s in args.sources]
+    if args.concurrent:
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(device)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+        for res in fit_sources_concurrently(sources, data, ncomp=args.ncomp, nwalkers=args.walkers, n_iter_burn=args.burn,
+                                            n_iter_walk=args.steps, seed=args.seed, device=device, outdir=outdir,
+                                            datapath=args.datapath, allow_synthetic=args.allow_synthetic):
+            if rank == 0:
+                print_summary(res, args.ncomp)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for source in sources[rank::world]:          # replicas only: one source per GPU at a time, no communication
         logger.info("Processing %s on GPU %d", source, device)
         res = fit_source(source, data, ncomp=args.ncomp, nwalkers=args.walkers, n_iter_burn=args.burn,

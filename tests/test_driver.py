@@ -120,3 +120,24 @@ def test_prefit_matches_scipy_on_the_oracle_model(oracle):
         res = minimize(nll, popt_ref, bounds=list(zip(lo, hi)), method="L-BFGS-B")
         assert nll(pmin) == pytest.approx(res.fun, rel=1e-3, abs=1e-4), (name, pmin, res.x)
         assert np.abs(pmin - res.x).max() < 0.05, (name, pmin, res.x)
+
+
+@pytest.mark.gpu
+def test_sources_fitted_concurrently_through_the_driver(tmp_path):
+    """BASELINE.json configs[3] at the driver level: three sources, one ensemble, one pickle per source in the
+    reference's layout; every source's chain stays inside its own bounds and finds a finite posterior."""
+    data = read_data(os.path.join(DATA_DIR, "flux.dat"))
+    names = list(data)[:3]
+    out = driver.fit_sources_concurrently(names, data, ncomp=1, nwalkers=40, n_iter_burn=10, n_iter_walk=15,
+                                          outdir=str(tmp_path), allow_synthetic=True)
+    assert [r["source"] for r in out] == names
+    for r in out:
+        assert r["chain"].shape == (15, 40, 4) and r["lnprobability"].shape == (15, 40)
+        b = r["bounds"]
+        assert np.all((r["chain"] >= b[:, 0]) & (r["chain"] <= b[:, 1]))
+        assert np.isfinite(r["lnprobability"]).mean() > 0.9 and 0.05 < r["acceptance_fraction"] < 0.95
+        with open(r["pickle"], "rb") as f:
+            tup = pickle.load(f)
+        assert len(tup) == 8 and tup[0] == r["source"]
+        np.testing.assert_array_equal(tup[-1][0], r["chain"])
+    assert len({tuple(r["bounds"][1]) for r in out}) == 3          # every source has its own background temperature

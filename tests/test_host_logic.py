@@ -133,3 +133,33 @@ def test_radex_errors():
     assert (R.tbg, R.deltav, R.escapeProbGeom) == (10.0, 5.0, "sphere")
     bb = R.background_brightness
     assert bb.shape == (40,) and (bb > 0).all()
+
+
+def test_synthetic_table_is_recognised_and_the_driver_refuses_it(tmp_path):
+    """the shipped co.dat is a synthetic table; nothing may fit real data with it silently."""
+    from radex_emcee_b200.radex import is_synthetic_table
+    from radex_emcee_b200.synth_lamda import default_path, rotor_path
+    assert is_synthetic_table(default_path()) and is_synthetic_table(rotor_path())
+    real = tmp_path / "co.dat"
+    real.write_text("!MOLECULE\nCO\n!MOLECULAR WEIGHT\n28.0\n")
+    assert not is_synthetic_table(str(real)) and not is_synthetic_table(str(tmp_path / "missing.dat"))
+    from radex_emcee_b200 import driver
+    import inspect
+    assert "allow_synthetic" in inspect.signature(driver.fit_source).parameters
+    assert "datapath" in inspect.signature(driver.fit_sources_concurrently).parameters
+
+
+def test_walkers_independent_is_emcee_s_check():
+    from radex_emcee_b200.sampler import walkers_independent
+    rng = np.random.default_rng(0)
+    good = rng.standard_normal((40, 4)) * [1e-3, 1.0, 1e3, 1e-6] + [4.0, 1.4, 17.8, -9.85]
+    assert walkers_independent(good)                        # scale does not matter: columns are normalised
+    dep = good.copy()
+    dep[:, 3] = 2.0 * dep[:, 1] - 0.5 * dep[:, 0]
+    assert not walkers_independent(dep)
+    const = good.copy()
+    const[:, 2] = 16.0          # a constant whose mean is exact (emcee compares the centred column with 0)
+    assert not walkers_independent(const)
+    nan = good.copy()
+    nan[3, 1] = np.nan
+    assert not walkers_independent(nan)
