@@ -1826,7 +1826,8 @@ int rb_solve_batch(rb_ctx *ctx, int64_t n, const double *tkin, const double *den
 }
 
 struct rb_srcset {
-  rb_ctx *ctx = nullptr;
+  rb_ctx *ctx = nullptr;           // identity check only; never dereferenced after creation (the set may outlive it)
+  int device = 0;
   int ncomp = 1, nsrc = 0;
   rb_source *d = nullptr;          // device table
   std::vector<rb_source> h;        // host copy (argument checks; row 0 drives the single-source pipeline)
@@ -2079,6 +2080,7 @@ int rb_srcset_create(rb_ctx *ctx, int32_t ncomp, int32_t nsrc, const rb_source *
   CUDA_TRY(cudaSetDevice(ctx->device));
   rb_srcset *set = new rb_srcset();
   set->ctx = ctx;
+  set->device = ctx->device;
   set->ncomp = ncomp;
   set->nsrc = nsrc;
   set->h.assign(src, src + nsrc);
@@ -2096,7 +2098,7 @@ int rb_srcset_create(rb_ctx *ctx, int32_t ncomp, int32_t nsrc, const rb_source *
 void rb_srcset_destroy(rb_srcset *set) {
   if (!set) return;
   if (set->d) {
-    cudaSetDevice(set->ctx->device);
+    cudaSetDevice(set->device);
     cudaFree(set->d);
   }
   delete set;

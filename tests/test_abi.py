@@ -96,3 +96,30 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("oracle/radex_oracle.c ro_", "").replace("oracle ro_", ""), f
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors in _lib.py against what a C compiler makes of include/radex_b200.h (plain C, no CUDA needed)."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "radex_b200.h"
+#define P(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+  printf("rb_opts %zu\n", sizeof(rb_opts));   P(rb_opts, kernel); P(rb_opts, abs_tol); P(rb_opts, thc_epi); P(rb_opts, park_max); P(rb_opts, lnprob_pipe_min);
+  printf("rb_obs %zu\n", sizeof(rb_obs));     P(rb_obs, jup); P(rb_obs, flux); P(rb_obs, eflux);
+  printf("rb_source %zu\n", sizeof(rb_source)); P(rb_source, bounds); P(rb_source, tbg); P(rb_source, has_td); P(rb_source, t_d);
+  printf("rb_split %zu\n", sizeof(rb_split)); P(rb_split, walkers_per_source); P(rb_split, block); P(rb_split, randomize); P(rb_split, seed);
+  return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(line.rsplit(" ", 1) for line in subprocess.check_output([str(exe)], text=True).strip().splitlines())
+    for name, ct in (("rb_opts", _lib.rb_opts), ("rb_obs", _lib.rb_obs), ("rb_source", _lib.rb_source), ("rb_split", _lib.rb_split)):
+        assert int(got[name]) == C.sizeof(ct), name
+        for key, off in got.items():
+            if key.startswith(name + "."):
+                assert int(off) == getattr(ct, key.split(".")[1]).offset, key

@@ -165,3 +165,19 @@ def test_world_size_2_matches_single_process(tmp_path, kw):
     x, l = ref.get_last_sample()
     np.testing.assert_array_equal(got["last_x"], x)
     np.testing.assert_array_equal(got["last_l"], l)
+
+
+def test_split_bijection_property():
+    """For any block size, seed and step the keyed map is a bijection of [0, block) (hypothesis)."""
+    from hypothesis import given, settings, strategies as st
+    from radex_emcee_b200.sampler import SplitSpec
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 300).map(lambda k: 2 * k), st.integers(0, 2 ** 64 - 1), st.integers(0, 2 ** 40), st.integers(0, 5))
+    def check(block, seed, step, blk):
+        sp = SplitSpec(block * 6, block * 6, block, True, seed)
+        i0 = ref_engine.slot_walker(sp, step, 0, blk * block, np.arange(block // 2))
+        i1 = ref_engine.slot_walker(sp, step, 1, blk * block, np.arange(block // 2))
+        assert sorted(np.concatenate([i0, i1]).tolist()) == list(range(block))
+
+    check()
