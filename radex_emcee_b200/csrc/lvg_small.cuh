@@ -202,7 +202,7 @@ __device__ __forceinline__ void lead_back2(double &Y0, double &Y1, double &F1, d
 }
 
 template <int KP>
-__device__ __forceinline__ double lead_solve2(double *sm, const int hl) {
+__device__ __forceinline__ double lead_solve2(double *sm, const int hl, long long *tmid = nullptr) {
   using L = Lay<KP>;
   constexpr int n = L::N;
   static_assert(n > 16 && n <= 32 && L::G == 16, "two rows per lane: 17 .. 32 lead levels in a half-warp");
@@ -221,6 +221,9 @@ __device__ __forceinline__ double lead_solve2(double *sm, const int hl) {
   double *pbase = sm + L::S_PB, *vtb = sm + L::S_VT;
   lead_pivots2<n - 1, n>(q0, q1, r0, r1, pbase, vtb, hl);
   __syncwarp();   // Vt complete
+#ifdef V2S_TIMING
+  if (tmid) *tmid = clock64();
+#endif
   constexpr int nf = NL - n, pitch = MP - n;
   const int l1 = hl + 16;
   const double *vt0 = vtb + hl * (hl - 1) / 2;
@@ -241,11 +244,11 @@ __device__ __forceinline__ double lead_solve2(double *sm, const int hl) {
 
 // v2::lead_solve for the G lanes of one model and a lead block of N = 4 KP levels.
 template <int KP>
-__device__ __forceinline__ double lead_solve(double *sm, const int hl) {
+__device__ __forceinline__ double lead_solve(double *sm, const int hl, long long *tmid = nullptr) {
   using L = Lay<KP>;
   constexpr int n = L::N, G = L::G;
   if constexpr (n > G) {
-    return lead_solve2<KP>(sm, hl);
+    return lead_solve2<KP>(sm, hl, tmid);
   } else {
     double *B = sm + L::S_LEAD;
     double q[n];
@@ -261,6 +264,9 @@ __device__ __forceinline__ double lead_solve(double *sm, const int hl) {
     double *pbase = sm + L::S_PB, *vtb = sm + L::S_VT;
     lead_pivots<n - 1, 1, n, G>(q, rmine, pbase, vtb, hl);
     __syncwarp();   // Vt complete
+#ifdef V2S_TIMING
+    if (tmid) *tmid = clock64();
+#endif
     // frozen levels: lane hl owns n + hl and, in a half-warp (29 or 25 of them), n + 16 + hl
     constexpr int nf = NL - n, pitch = MP - n;
     const double *vt = vtb + ((hl < n) ? hl * (hl - 1) / 2 : 0);   // lanes >= n only go through the motions: stay inside the slab

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "internal.h"
@@ -795,10 +796,19 @@ __global__ void k_sched_scatter(const int *keys, long long n, unsigned long long
 
 
 // ---- cached engines per lead-block size (lvg_small.cuh): G = 16 lanes per model up to 16 lead levels, else 32 ----
+#ifdef V2S_TIMING
+// debug build only (tools/timing.sh): cycles per section of the engine loop, summed over warps: [KP][0..7] = load, patch,
+// pivots, back-substitution, relax, lines, rest of the loop body, iterations
+__device__ unsigned long long g_tm[8][8];
+#define TM(var) const long long var = clock64()
+#else
+#define TM(var)
+#endif
 template <int KP>
 __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDev mol, SolveCfg cfg, SolveIO io) {
   using namespace v2s;
   using L = Lay<KP>;
+  static_assert(v2::IT_DECIDE >= 1, "the engines never run a model's first call (it == 0 has its own arithmetic in v2::solve)");
   constexpr int G = L::G, NT = L::NT;
   constexpr int SSLAB = L::SSLAB, S_LEAD = L::S_LEAD, S_M = L::S_M, S_X = L::S_X, S_XNEW = L::S_XNEW, S_BETA = L::S_BETA,
                 S_DNB = L::S_DNB, S_UPB = L::S_UPB, S_TEX = L::S_TEX;
@@ -826,6 +836,14 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
   // a slab that never receives a model still runs the arithmetic of its warp: give it finite numbers
   for (int e = hl; e < SSLAB; e += G) sm[e] = 1.0;
   __syncthreads();
+  // trips over the lines (tt: lines G tt .. G tt + G - 1) that hold a lead line, i.e. a line whose escape probability can
+  // differ from 1 while the model stays in this engine.  A CO-like table (line l: l + 1 -> l) has its 4 KP - 1 lead lines
+  // in the first trip (KP <= 4) or the first two: the loop then evaluates escprob for those trips only (LEAD_FAST).
+  unsigned lead_trips = 0;
+  for (int l = 0; l < nn; ++l)
+    if (max(lmn[l] & 0xff, (lmn[l] >> 8) & 0xff) < 4 * KP) lead_trips |= 1u << (l / G);
+  constexpr unsigned LEAD_FAST = (G == 16 && KP > 4) ? 3u : 1u, LEAD_ALL = (1u << NT) - 1u;
+  const bool lead_fast = (lead_trips & ~LEAD_FAST) == 0;
   // queue: the positions of key KP in the sorted order (heaviest key first; key 3 is the last block)
   const unsigned long long p_begin = io.sched_small[16 + KP], p_end = io.sched_small[(KP == 3) ? 48 : 16 + KP - 1];
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
@@ -837,7 +855,12 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
   unsigned flags = 0;   // bit t: line hl + 16 t had tau > 0.01f after the last call (RADEX's own stop rule)
   double cdmol = 1.0, cddv = 1.0;
   unsigned long long iters = 0, n_cached = 0, n_models = 0, n_inval = 0;
+#ifdef V2S_TIMING
+  unsigned long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tm_prev = clock64();
+#endif
   for (;;) {
+    TM(tm0);
     // ---- a free half takes the next model of the queue -------------------------------------------------------------
     if (!active && !exhausted) {
       unsigned long long t = 0;
@@ -883,6 +906,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
       ++n_models;
     }
     __syncwarp();
+    TM(tm1);
     // ---- one call of matrix(): radiative rates of the lead lines, lead block, M -------------------------------
     double *B = sm + S_LEAD;
 #pragma unroll
@@ -899,8 +923,15 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
       }
     }
     __syncwarp();
+    TM(tm2);
+#ifdef V2S_TIMING
+    long long tmid = 0;
+    const double tot = lead_solve<KP>(sm, hl, &tmid);
+#else
     const double tot = lead_solve<KP>(sm, hl);
+#endif
     __syncwarp();
+    TM(tm3);
     const double rtot = v2::rcp1(tot);
     // ---- normalise, floor, under-relax + pyradex's stop test (v2::solve: lane l of 32 owns levels l and l + 32;
     // in a half-warp lane hl stands for lanes hl (dA) and hl + 16 (dB) of that warp)
@@ -909,48 +940,91 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     for (int t = 0; t < ((G == 16) ? 3 : 2); ++t) {
       const int i = hl + ((t == 0) ? 0 : (t == 1) ? 32 : 16);
       if (i < NL) {
-        const double xn = fmax(RB_MINPOP, sm[S_XNEW + i] * rtot);
+        const double xn = fmax(v2::KC[v2::KC_MINPOP], sm[S_XNEW + i] * rtot);
         const double prev = sm[S_X + i];
-        const double xo = (it == 0) ? xn : fmax(RB_MINPOP, prev);
-        const double xr = RB_F32(0.3) * xn + RB_F32(0.7) * xo;
+        const double xo = fmax(v2::KC[v2::KC_MINPOP], prev);   // it >= IT_DECIDE >= 1 here: never the first call
+        const double xr = v2::KC[v2::KC_F03] * xn + v2::KC[v2::KC_F07] * xo;
         sm[S_XNEW + i] = xn;
         sm[S_X + i] = xr;
         if (t == 2) dB += fabs(prev - xr); else dA += fabs(prev - xr);
       }
     }
-    const double diff = (G == 16) ? group_sum<G>(dA + dB) : group_sum<G>(dA);
     __syncwarp();
+    TM(tm4);
     // ---- per line: Tex of this call, optical depth and escape probability of the next ------------------------
-    double tsA = 0.0, tsB = 0.0;
+    // Straight-line code over the NT trips (no branch per line or per trip): the logarithm of every trip's Tex and the
+    // exponential of every trip's escape probability are independent dependency chains that the scheduler interleaves;
+    // with a branch around each they ran one after the other and their latency was a third of the whole call.
+    // The arithmetic per line is unchanged (a floored or out-of-range line computes on clamped inputs and discards).
     const int nthick_this = nthick;
     nthick = 0;
     topthick = -1;
     unsigned nflags = 0;
+    double diff = 0.0, tsA = 0.0, tsB = 0.0;
+    auto lines = [&](auto em) {
+      constexpr unsigned EM = decltype(em)::value;   // trips whose lines get their escape probability evaluated
+      int ll[NT], lm[NT], ln[NT];
+      bool lvalid[NT], lfloored[NT];
+      double ltold[NT], larg[NT], ltaur[NT], ltex[NT], lmid[NT];
+      bool thick_any = false;
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      // half-warp: lines hl, hl + 32 (tsA), hl + 16 (tsB): the order of the 32-lane sums
-      const int tt = (G == 16) ? ((t == 0) ? 0 : (t == 1) ? 2 : 1) : t;
-      const int l = hl + G * tt;
-      if (l < nn) {
-        const int mn = lmn[l];
-        const int m = mn & 0xff, nlo = (mn >> 8) & 0xff;
-        const double gr = cs[C_LGR + l];
-        const double xm = sm[S_XNEW + m], xn = sm[S_XNEW + nlo];
-        const bool floored = (xn <= RB_MINPOP) || (xm <= RB_MINPOP);
-        const double told = sm[S_TEX + l];
-        double thistex = told;
-        if (!floored) thistex = cs[C_LFKXNU + l] * v2::rcp1(v2::fast_log(xn * gr * v2::rcp1(xm)));
-        if (cfg.stop_rule == RB_STOP_RADEX && ((flags >> tt) & 1u)) {
-          if (G == 16 && tt == 1) tsB += fabs((thistex - told) / thistex); else tsA += fabs((thistex - told) / thistex);
+      for (int t = 0; t < NT; ++t) {
+        // half-warp: lines hl, hl + 32 (tsA), hl + 16 (tsB): the order of the 32-lane sums
+        const int tt = (G == 16) ? ((t == 0) ? 0 : (t == 1) ? 2 : 1) : t;
+        const int l = hl + G * tt;
+        lvalid[t] = l < nn;
+        ll[t] = lvalid[t] ? l : 0;
+        const int mn = lmn[ll[t]];
+        lm[t] = mn & 0xff;
+        ln[t] = (mn >> 8) & 0xff;
+        const double gr = cs[C_LGR + ll[t]];
+        const double xm = sm[S_XNEW + lm[t]], xn = sm[S_XNEW + ln[t]];
+        lfloored[t] = (xn <= v2::KC[v2::KC_MINPOP]) || (xm <= v2::KC[v2::KC_MINPOP]);
+        ltold[t] = sm[S_TEX + ll[t]];
+        larg[t] = xn * gr * v2::rcp1(xm);
+        const double tau = cddv * (sm[S_X + ln[t]] * gr - sm[S_X + lm[t]]) * cs[C_LTDEN + ll[t]];
+        ltaur[t] = tau * 0.5;
+        if (lvalid[t]) {
+          if (tau > v2::KC[v2::KC_D001]) ++nthick;
+          if (tau > v2::KC[v2::KC_F001]) nflags |= 1u << tt;
+          if (!(fabs(ltaur[t]) < v2::KC[v2::KC_F001])) topthick = max(topthick, max(lm[t], ln[t]));
+          if (((EM >> tt) & 1u) && !(fabs(ltaur[t]) < 7.0)) thick_any = true;
         }
-        sm[S_TEX + l] = (it == 0) ? thistex : 0.5 * (thistex + told);
-        const double tau = cddv * (sm[S_X + nlo] * gr - sm[S_X + m]) * cs[C_LTDEN + l];
-        if (tau > 1.0e-2) ++nthick;
-        if (tau > RB_F32(0.01)) nflags |= 1u << tt;
-        if (!(fabs(tau * 0.5) < RB_F32(0.01))) topthick = max(topthick, max(m, nlo));
-        sm[S_BETA + l] = v2::escprob_fast(tau, RB_GEOM_LVG);
       }
-    }
+      diff = (G == 16) ? group_sum<G>(dA + dB) : group_sum<G>(dA);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) ltex[t] = cs[C_LFKXNU + ll[t]] * v2::rcp1(v2::fast_log(larg[t]));
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int tt = (G == 16) ? ((t == 0) ? 0 : (t == 1) ? 2 : 1) : t;
+        lmid[t] = ((EM >> tt) & 1u) ? v2::escprob_lvg_mid(ltaur[t]) : 1.0;
+      }
+      if (__any_sync(0xffffffffu, thick_any)) {   // a line with |tau/2| >= 7 (or NaN) somewhere in the warp: escprob's third branch
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int tt = (G == 16) ? ((t == 0) ? 0 : (t == 1) ? 2 : 1) : t;
+          if ((EM >> tt) & 1u) {
+            const double bl = v2::escprob_lvg_thick(ltaur[t]);
+            if (!(fabs(ltaur[t]) < 7.0)) lmid[t] = bl;
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int tt = (G == 16) ? ((t == 0) ? 0 : (t == 1) ? 2 : 1) : t;
+        const double thistex = lfloored[t] ? ltold[t] : ltex[t];
+        if (cfg.stop_rule == RB_STOP_RADEX && lvalid[t] && ((flags >> tt) & 1u)) {
+          if (G == 16 && tt == 1) tsB += fabs((thistex - ltold[t]) / thistex); else tsA += fabs((thistex - ltold[t]) / thistex);
+        }
+        if (lvalid[t]) {
+          sm[S_TEX + ll[t]] = 0.5 * (thistex + ltold[t]);
+          // a trip without lead lines keeps beta = 1 (its lines are frozen; if one turns thick the model leaves this engine
+          // and the leave path below evaluates escprob for it)
+          if ((EM >> tt) & 1u) sm[S_BETA + ll[t]] = (fabs(ltaur[t]) < v2::KC[v2::KC_F001]) ? 1.0 : lmid[t];
+        }
+      }
+    };
+    if (lead_fast) lines(std::integral_constant<unsigned, LEAD_FAST>()); else lines(std::integral_constant<unsigned, LEAD_ALL>());
     flags = nflags;
     topthick = group_max_int(hmask, topthick);
     bool stop;
@@ -967,6 +1041,14 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
       stop = (diff < cfg.abs_tol) && (it > cfg.miniter);
     }
     __syncwarp();
+#ifdef V2S_TIMING
+    {
+      const long long tm5 = clock64();
+      tm[0] += tm1 - tm0; tm[1] += tm2 - tm1; tm[2] += tmid - tm2; tm[3] += tm3 - tmid; tm[4] += tm4 - tm3; tm[5] += tm5 - tm4;
+      tm[6] += tm0 - tm_prev; tm[7] += 1;
+      tm_prev = tm5;
+    }
+#endif
     if (!active) continue;
     ++n_cached;
     // ---- what v2::solve decides at the bottom of this call and at the top of the next ---------------------------
@@ -985,8 +1067,12 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
       for (int t = 0; t < NT; ++t) {
         const int l = hl + G * t;
         if (l < nn) {
+          // escape probability of the next call for EVERY line (the loop keeps it only for the trips with lead lines):
+          // the expressions of the loop, from the same relaxed populations
+          const int m = lmn[l] & 0xff, nlo = (lmn[l] >> 8) & 0xff;
+          const double tau = cddv * (sm[S_X + nlo] * cs[C_LGR + l] - sm[S_X + m]) * cs[C_LTDEN + l];
           st[41 + l] = sm[S_TEX + l];
-          st[81 + l] = sm[S_BETA + l];
+          st[81 + l] = v2::escprob_fast(tau, RB_GEOM_LVG);
         }
         const unsigned b = __ballot_sync(hmask, (flags >> t) & 1u);
         bits |= (unsigned long long)((G == 32) ? b : (b >> (16 * half)) & 0xffffu) << (G * t);
@@ -1043,6 +1129,10 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     __syncwarp(hmask);
   }
   (void)qnan;
+#ifdef V2S_TIMING
+  if (lane == 0)
+    for (int i = 0; i < 8; ++i) atomicAdd(&g_tm[KP][i], tm[i]);
+#endif
   if (hl == 0) {
     if (iters) atomicAdd(&io.counters[1], iters);
     if (cfg.stats && n_models) {
@@ -2375,6 +2465,18 @@ static int stretch_run_impl(rb_ctx *ctx, const rb_srcset *set, const rb_split *s
   }
   return RB_OK;
 }
+
+#ifdef V2S_TIMING
+int rb_debug_timing(unsigned long long *out64, int reset) {
+  cudaDeviceSynchronize();
+  if (out64) cudaMemcpyFromSymbol(out64, g_tm, sizeof(unsigned long long) * 64);
+  if (reset) {
+    static unsigned long long z[64];
+    cudaMemcpyToSymbol(g_tm, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int rb_fp64_peak(rb_ctx *ctx, double *tflops) {
   if (!ctx || !tflops) return RB_ERR_ARG;
