@@ -61,7 +61,11 @@ typedef struct rb_opts {
   double thc_epi;      /* 2 h c     used by the brightness epilogue                        */
   int32_t park_max;    /* 0 = automatic.  3..7: largest lead block (in panels of 4 levels) that gets a cached-engine
                           launch of its own in a scheduled batch (tests force 7 on small batches)            */
-  int32_t reserved;
+  int32_t spec_half;   /* rb_stretch_run_dev: propose the second half-step speculatively (both candidates per walker: its
+                          partner moved / stayed) so that a step is ONE lnprob launch of 1.5 N walkers -- same chain
+                          bit for bit, half the latency.  0 = automatic (while the 1.5 N candidates are at most 17 warps
+                          per SM: ~1600 walkers on a B200), -1 = never, 1 = whenever the half-ensemble runs as one fused
+                          launch                                                                              */
   int64_t lnprob_pipe_min; /* 0 = automatic (8192).  walkers per call from which lnprob runs as
                           expand -> scheduled solve -> combine instead of one fused launch          */
 } rb_opts;

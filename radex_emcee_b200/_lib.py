@@ -23,7 +23,7 @@ class RadexB200Error(RuntimeError):
 class rb_opts(C.Structure):
     _fields_ = [("stop_rule", C.c_int32), ("miniter", C.c_int32), ("maxiter", C.c_int32), ("kernel", C.c_int32),
                 ("abs_tol", C.c_double), ("fk_epi", C.c_double), ("thc_epi", C.c_double),
-                ("park_max", C.c_int32), ("reserved", C.c_int32), ("lnprob_pipe_min", C.c_int64)]
+                ("park_max", C.c_int32), ("spec_half", C.c_int32), ("lnprob_pipe_min", C.c_int64)]
 
 
 class rb_obs(C.Structure):

@@ -695,6 +695,8 @@ __global__ void __launch_bounds__(256) k_lnprob_v1(MolDev mol, SolveCfg cfg, Lnp
 // and the engine launches overlapping): 1 component, 8192 walkers per call 4.35e6 vs 3.64e6; 2 components, 8192 per call
 // 1.86e6 vs 1.66e6, 16384 per call 2.49e6 vs 1.80e6
 #define RB_LNPROB_PIPE_MIN 8192
+// rb_stretch_run_dev proposes the second half-step speculatively while 3 x (walkers / 2) candidates are at most this many warps per SM
+#define RB_SPEC_WARPS_PER_SM 17
 
 __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, SolveCfg cfg, SolveIO io) {
   extern __shared__ double smem[];
@@ -1179,7 +1181,7 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lnprob_v2(MolDev mol, Solv
         lnprob_dens(mol, pow(10.0, p[4 * c + 0]), dens);
         int st = 0;
         const double cdmol = pow(10.0, p[4 * c + 2]);
-        const int it = v2::solve(mol, sm, gB, phase, lane, pow(10.0, p[4 * c + 1]), dens, cdmol, tbg, cfg, &st);
+        const int it = v2::solve<true>(mol, sm, gB, phase, lane, pow(10.0, p[4 * c + 1]), dens, cdmol, tbg, cfg, &st);
         if (st & (RB_ST_T_RANGE | RB_ST_N_RANGE)) {
           value_error = true;  // ValueError -> -inf (emcee_radex.py:134-137)
         } else {
@@ -1475,7 +1477,7 @@ void rb_default_opts(rb_opts *o) {
   o->fk_epi = 1.4387768775039338;
   o->thc_epi = 3.9728917142978115e-16;
   o->park_max = 0;
-  o->reserved = 0;
+  o->spec_half = 0;
   o->lnprob_pipe_min = 0;
 }
 
@@ -2315,6 +2317,40 @@ static int stretch_one_step(rb_ctx *ctx, const rb_srcset *set, const st2::SplitD
   return RB_OK;
 }
 
+// The same step with the second half-step proposed speculatively (stretch.cuh: k_propose_spec): one lnprob launch of
+// 3 nhalf models per step.  Buffers: C1, Cold [nhalf x ndim]; Q3 [3 nhalf x ndim] = Q0 | Qa | Qb;
+// L3 [3 nhalf]; logfac0, logfac1 [nhalf]; jpart, acc0 [nhalf]; the selected candidates overwrite C1 / its lnprob L3's head.
+struct SpecBufs {
+  double *C1, *Cold, *Q3, *L3, *logfac0, *logfac1, *Lsel;
+  int *jpart, *acc0, *src3;   // src3 [3 nhalf]: source row of every candidate (several sources in one ensemble)
+};
+static int stretch_one_step_spec(rb_ctx *ctx, const rb_srcset *set, const st2::SplitDev &sp, const rb_split *split, double a,
+                                 const rb_opts *opts, long long N, int ndim, double *X, double *lnp, long long *naccept,
+                                 unsigned long long *counters, const SpecBufs &b, unsigned long long *d_step) {
+  const long long nhalf = N / 2;
+  const int tpb = 128;
+  const unsigned nb = (unsigned)((nhalf + tpb - 1) / tpb);
+  cudaStream_t s = ctx->stream;
+  double *Q0 = b.Q3, *Qa = b.Q3 + nhalf * ndim, *Qb = b.Q3 + 2 * nhalf * ndim;
+  st2::k_pack<<<nb, tpb, 0, s>>>(sp, d_step, 0, 1, 0, nhalf, ndim, X, b.C1);
+  int *src3 = (set->nsrc > 1) ? b.src3 : nullptr;
+  st2::k_propose2<<<nb, tpb, 0, s>>>(sp, d_step, 0, 0, 0, nhalf, ndim, X, b.C1, a, split->seed, Q0, b.logfac0, src3);
+  st2::k_pack<<<nb, tpb, 0, s>>>(sp, d_step, 0, 0, 0, nhalf, ndim, X, b.Cold);
+  st2::k_propose_spec<<<nb, tpb, 0, s>>>(sp, d_step, 0, 0, nhalf, ndim, X, b.Cold, Q0, a, split->seed, Qa, Qb, b.logfac1, b.jpart,
+                                         src3 ? src3 + nhalf : nullptr, src3 ? src3 + 2 * nhalf : nullptr);
+  int rc = lnprob_core(ctx, set->ncomp, 3 * nhalf, b.Q3, set->d, set->nsrc, set->h[0], src3, opts, b.L3);
+  if (rc != RB_OK) return rc;
+  st2::k_accept2<<<nb, tpb, 0, s>>>(sp, d_step, 0, 0, 0, nhalf, ndim, X, lnp, Q0, b.L3, b.logfac0, split->seed, naccept, counters,
+                                    ctx->counters + 2, counters ? counters + 1 : nullptr, b.acc0);
+  st2::k_select_spec<<<nb, tpb, 0, s>>>(nhalf, ndim, b.acc0, b.jpart, Qa, Qb, b.L3 + nhalf, b.L3 + 2 * nhalf, b.C1, b.Lsel);
+  st2::k_accept2<<<nb, tpb, 0, s>>>(sp, d_step, 0, 1, 0, nhalf, ndim, X, lnp, b.C1, b.Lsel, b.logfac1, split->seed, naccept,
+                                    counters, nullptr, nullptr);
+  st2::k_step_inc<<<1, 1, 0, s>>>(d_step);
+  ctx->launches += 9;
+  CUDA_TRY(cudaGetLastError());
+  return RB_OK;
+}
+
 static int stretch_run_impl(rb_ctx *ctx, const rb_srcset *set, const rb_split *split, double a, uint64_t step0,
                             int64_t nsteps, const rb_opts *opts, double *X, double *lnp, int64_t *naccept,
                             int64_t *counters, int32_t thin, double *chain, double *lnp_chain);
@@ -2364,7 +2400,15 @@ static int stretch_run_impl(rb_ctx *ctx, const rb_srcset *set, const rb_split *s
   const long long nhalf = N / 2;
   const size_t b_c = align256((size_t)nhalf * ndim * sizeof(double)), b_v = align256((size_t)nhalf * sizeof(double));
   const size_t b_i = align256((size_t)nhalf * sizeof(int));
-  const size_t b_all = 2 * b_c + 2 * b_v + b_i + 256;
+  // speculative second half-step while the three candidates of every slot can run side by side (one warp each; measured
+  // on B200, walker-steps/s with / without: 100 walkers 2.57e5 / 1.35e5, 800: 1.28e6 / 9.4e5, 1600: 1.74e6 / 1.51e6,
+  // 3200: 2.22e6 / 2.38e6; two components, 800 walkers: 3.97e5 / 2.54e5), unless rb_opts.spec_half says otherwise
+  rb_opts od;
+  rb_default_opts(&od);
+  if (opts) od = *opts;
+  const bool spec_fits = od.spec_half > 0 || (od.spec_half == 0 && 3 * nhalf <= (long long)RB_SPEC_WARPS_PER_SM * ctx->sm_count);
+  const size_t b_spec = spec_fits ? (5 * b_c + 6 * b_v + 5 * b_i) : 0;
+  const size_t b_all = 2 * b_c + 2 * b_v + b_i + 256 + b_spec;
   if (b_all > ctx->samp_bytes) {
     if (ctx->samp_graph) {
       cudaGraphExecDestroy(ctx->samp_graph);
@@ -2381,13 +2425,29 @@ static int stretch_run_impl(rb_ctx *ctx, const rb_srcset *set, const rb_split *s
   double *logfac = reinterpret_cast<double *>(base + 2 * b_c), *lnp_new = reinterpret_cast<double *>(base + 2 * b_c + b_v);
   int *src_id = reinterpret_cast<int *>(base + 2 * b_c + 2 * b_v);
   unsigned long long *d_step = reinterpret_cast<unsigned long long *>(base + 2 * b_c + 2 * b_v + b_i);
+  SpecBufs sb{};
+  if (spec_fits) {
+    char *q = base + 2 * b_c + 2 * b_v + b_i + 256;
+    sb.C1 = reinterpret_cast<double *>(q); q += b_c;
+    sb.Cold = reinterpret_cast<double *>(q); q += b_c;
+    sb.Q3 = reinterpret_cast<double *>(q); q += 3 * b_c;   // three blocks of nhalf x ndim, contiguous: b_c is padded, so
+    sb.L3 = reinterpret_cast<double *>(q); q += 3 * b_v;   // the blocks are addressed by nhalf * ndim, not by b_c
+    sb.logfac0 = reinterpret_cast<double *>(q); q += b_v;
+    sb.logfac1 = reinterpret_cast<double *>(q); q += b_v;
+    sb.Lsel = reinterpret_cast<double *>(q); q += b_v;
+    sb.jpart = reinterpret_cast<int *>(q); q += b_i;
+    sb.acc0 = reinterpret_cast<int *>(q); q += b_i;
+    sb.src3 = reinterpret_cast<int *>(q); q += 3 * b_i;   // addressed by nhalf (b_i is padded)
+  }
   cudaStream_t s = ctx->stream;
   const unsigned long long step0_ = step0;
   CUDA_TRY(cudaMemcpyAsync(d_step, &step0_, sizeof(step0_), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaStreamSynchronize(s));   // step0_ lives on this stack frame
   unsigned long long *cnt = reinterpret_cast<unsigned long long *>(counters);
   long long *nacc = reinterpret_cast<long long *>(naccept);
+  bool spec = false;   // decided below, once it is known that the half-ensemble runs as one fused launch
   auto step_once = [&]() {
+    if (spec) return stretch_one_step_spec(ctx, set, sp, split, a, opts, N, ndim, X, lnp, nacc, cnt, sb, d_step);
     return stretch_one_step(ctx, set, sp, split, a, opts, N, ndim, X, lnp, nacc, cnt, Cbuf, Q, logfac, lnp_new,
                             (set->nsrc > 1) ? src_id : nullptr, d_step);
   };
@@ -2405,6 +2465,10 @@ static int stretch_run_impl(rb_ctx *ctx, const rb_srcset *set, const rb_split *s
   const SolveCfg cfg = make_cfg(ctx, opts, 1.0, set->h[0].tbg, RB_GEOM_LVG);
   const bool fused = !(set->nsrc == 1 && use_v2(ctx, opts) && cfg.sched && cfg.small && cfg.cache &&
                        nhalf >= cfg.lnprob_pipe_min && nhalf * set->ncomp >= RB_SCHED_MIN);
+  // (forced speculation on a large ensemble: the 1.5 N candidates must still be one fused launch, not the pipeline)
+  spec = fused && spec_fits &&
+         !(set->nsrc == 1 && use_v2(ctx, opts) && cfg.sched && cfg.small && cfg.cache && 3 * nhalf >= cfg.lnprob_pipe_min &&
+           3 * nhalf * set->ncomp >= RB_SCHED_MIN);
   int64_t k = 0;
   if (fused && nsteps >= 3) {
     struct Key {
@@ -2448,7 +2512,7 @@ static int stretch_run_impl(rb_ctx *ctx, const rb_srcset *set, const rb_split *s
       }
       ctx->samp_key.assign(kb, kb + sizeof(key));
     }
-    const long long per_step = 2 * 4 + 1;   // pack, propose2, lnprob, accept2 per half-step + the step counter
+    const long long per_step = 2 * 4 + 1;   // pack, propose2, lnprob, accept2 per half-step + the step counter (speculative: 9 as well)
     for (; k < nsteps; ++k) {
       CUDA_TRY(cudaGraphLaunch(ctx->samp_graph, s));
       ctx->launches += per_step;
@@ -2470,9 +2534,11 @@ static int stretch_run_impl(rb_ctx *ctx, const rb_srcset *set, const rb_split *s
 int rb_debug_timing(unsigned long long *out64, int reset) {
   cudaDeviceSynchronize();
   if (out64) cudaMemcpyFromSymbol(out64, g_tm, sizeof(unsigned long long) * 64);
+  if (out64) cudaMemcpyFromSymbol(out64 + 64, v2::g_tv, sizeof(unsigned long long) * 60);
   if (reset) {
     static unsigned long long z[64];
     cudaMemcpyToSymbol(g_tm, z, sizeof(z));
+    cudaMemcpyToSymbol(v2::g_tv, z, sizeof(unsigned long long) * 60);
   }
   return 0;
 }

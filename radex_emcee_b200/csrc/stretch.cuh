@@ -106,7 +106,7 @@ __global__ void k_accept2(SplitDev sp, const unsigned long long *step_ptr, unsig
                           long long gid_base, long long nhalf, int ndim, double *X, double *lnp, const double *Q,
                           const double *lnp_new, const double *logfac, unsigned long long seed, long long *naccept,
                           unsigned long long *nan_count, const unsigned long long *nsolves_src,
-                          unsigned long long *nsolves_sum) {
+                          unsigned long long *nsolves_sum, int *accepted = nullptr) {
   const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   int isnan_ = 0;
   if (k < nhalf) {
@@ -120,15 +120,66 @@ __global__ void k_accept2(SplitDev sp, const unsigned long long *step_ptr, unsig
     const double lnew = lnp_new[k];
     isnan_ = (lnew != lnew);
     const double lnpdiff = logfac[k] + lnew - lnp[i];
-    if (lnpdiff > lnu) {   // -inf - -inf = NaN compares false -> rejected, like numpy
+    const bool acc = lnpdiff > lnu;   // -inf - -inf = NaN compares false -> rejected, like numpy
+    if (acc) {
       for (int d = 0; d < ndim; ++d) X[i * ndim + d] = Q[k * ndim + d];
       lnp[i] = lnew;
       if (naccept) naccept[i] += 1;   // one slot per walker per half-step: no atomics needed
     }
+    if (accepted) accepted[k] = acc ? 1 : 0;
   }
   const unsigned nanb = __ballot_sync(0xffffffffu, isnan_);
   if ((threadIdx.x & 31) == 0 && nanb && nan_count) atomicAdd(nan_count, (unsigned long long)__popc(nanb));
   if (k == 0 && nsolves_sum && nsolves_src) atomicAdd(nsolves_sum, *nsolves_src);
+}
+
+// ---- speculative second half-step (small ensembles) -------------------------------------------------------------------
+// A step of a small ensemble is bound by the latency of ONE solve per half-step (config 1: 50 models on 148 SMs, ~100
+// sequential calls of matrix() each).  The second half-step depends on the first only through the partner c_j of every
+// proposal, and c_j is one of two known points: where it stood, or the first half-step's proposal for it.  So both
+// candidates are proposed before anything is solved, the nhalf + 2 nhalf models go through ONE lnprob launch, and after
+// the first half-step's accept/reject the candidate the sequential move would have made is selected.  Same random
+// numbers, same arithmetic per candidate: the chain is the sequential one bit for bit; a step costs one solve latency
+// and 1.5 times the solves.
+// Cold: the walkers of half 0 in slot order BEFORE their move (k_pack); Q0: half 0's proposals, same slot order.
+__global__ void k_propose_spec(SplitDev sp, const unsigned long long *step_ptr, unsigned long long step_, long long gid_base,
+                               long long nhalf, int ndim, const double *X, const double *Cold, const double *Q0, double a,
+                               unsigned long long seed, double *Qa, double *Qb, double *logfac, int *jpart, int *src_a,
+                               int *src_b) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= nhalf) return;
+  const int half = 1;
+  const unsigned long long step = step_of(step_ptr, step_);
+  const long long i = slot_walker(sp, step, half, gid_base, k);
+  const unsigned long long gid = (unsigned long long)(gid_base + i);
+  uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)(step * 2ULL + (unsigned)half),
+                   (uint32_t)((step * 2ULL + (unsigned)half) >> 32) & 0x7fffffffu};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const double u = u01(c[0], c[1]);
+  const double sq = __dadd_rn(__dmul_rn(a - 1.0, u), 1.0);
+  const double z = __dmul_rn(sq, sq) / a;
+  const long long src = (long long)(gid / (unsigned long long)sp.W), nc = sp.W >> 1;
+  long long j = (long long)(u01(c[2], c[3]) * (double)nc);
+  if (j >= nc) j = nc - 1;
+  j += src * nc;
+  for (int d = 0; d < ndim; ++d) {
+    const double s = X[i * ndim + d], co = Cold[j * ndim + d], cn = Q0[j * ndim + d];
+    Qa[k * ndim + d] = __dsub_rn(co, __dmul_rn(co - s, z));
+    Qb[k * ndim + d] = __dsub_rn(cn, __dmul_rn(cn - s, z));
+  }
+  logfac[k] = (ndim - 1.0) * log(z);
+  jpart[k] = (int)j;
+  if (src_a) src_a[k] = src_b[k] = (int)src;
+}
+
+// the candidate of slot k that the sequential move would have proposed: its partner moved (Qb) or stayed (Qa)
+__global__ void k_select_spec(long long nhalf, int ndim, const int *acc0, const int *jpart, const double *Qa, const double *Qb,
+                              const double *La, const double *Lb, double *Qsel, double *Lsel) {
+  const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= nhalf) return;
+  const bool moved = acc0[jpart[k]] != 0;
+  for (int d = 0; d < ndim; ++d) Qsel[k * ndim + d] = moved ? Qb[k * ndim + d] : Qa[k * ndim + d];
+  Lsel[k] = moved ? Lb[k] : La[k];
 }
 
 __global__ void k_step_inc(unsigned long long *step_ptr) { *step_ptr += 1ULL; }

@@ -130,7 +130,19 @@ def test_chain_matches_cpu_reference_sampler(setup, oracle, randomize):
     np.testing.assert_array_equal(gpu.get_chain(), py.get_chain())
     np.testing.assert_array_equal(gpu.get_log_prob(), py.get_log_prob())
     np.testing.assert_array_equal(gpu.acceptance_fraction, py.acceptance_fraction)
-    assert gpu.total_solves + int(gpu.engine.total_solves.item()) == int(py.engine.total_solves.item())
+    # 64 walkers: the in-library loop proposes the second half-step speculatively (rb_opts.spec_half = 0: automatic), one
+    # lnprob launch of 3 x 32 candidates per step -- same chain (above), more solves; with spec_half = -1 it is the
+    # sequential move launch for launch
+    n_py = int(py.engine.total_solves.item())
+    n_spec = gpu.total_solves + int(gpu.engine.total_solves.item())
+    assert n_py <= n_spec <= 1.5 * n_py + nw, (n_py, n_spec)
+    seq_model = SLEDModel(1, model.Jup, model.flux, model.eflux, model.bounds, model.tbg, opts=_lib.default_opts(spec_half=-1))
+    seq = StretchSampler(nw, 4, CudaEngine(ctx, seq_model), seed=42, randomize_split=randomize)
+    assert seq.native
+    seq.run_mcmc(pos, nsteps)
+    np.testing.assert_array_equal(seq.get_chain(), py.get_chain())
+    np.testing.assert_array_equal(seq.get_log_prob(), py.get_log_prob())
+    assert seq.total_solves + int(seq.engine.total_solves.item()) == n_py
     cpu = StretchSampler(nw, 4, ref_engine.NumpyEngine(
         ref_engine.oracle_lnprob1(oracle, model.Jup, model.flux, model.eflux, model.bounds, model.tbg)), seed=42,
         randomize_split=randomize)
@@ -275,3 +287,25 @@ def test_nccl_two_ranks_match_single_process(ctx, tmp_path):
     np.testing.assert_array_equal(got["chain"], ref.get_chain())
     np.testing.assert_array_equal(got["lnp"], ref.get_log_prob())
     np.testing.assert_array_equal(got["acc"], ref.acceptance_fraction)
+
+
+def test_speculative_half_step_with_several_sources(ctx):
+    """rb_opts.spec_half: the in-library loop proposes the second half-step speculatively (both candidates per walker, one
+    lnprob launch of 1.5 N walkers per step).  Four sources x 24 walkers, randomized split: the chain, the log-probabilities
+    and the per-walker acceptance counters equal those of the sequential move (spec_half = -1) bit for bit."""
+    data = read_data(ROOT + "/data/flux.dat")
+    chains = []
+    for spec in (0, -1, 1):
+        models, starts = [], []
+        for k, nm in enumerate(list(data)[:4]):
+            z, lw, jup, flux, eflux = get_source(nm, data)
+            tbg, ra, bounds, p0 = er1.source_setup(z)
+            models.append(SLEDModel(1, jup, flux, eflux, bounds, tbg, opts=_lib.default_opts(spec_half=spec)))
+            starts.append(p0 + 0.02 * np.random.default_rng(11 + k).standard_normal((24, 4)))
+        s = StretchSampler(96, 4, CudaEngine(ctx, models), seed=9, nsources=4)
+        assert s.native
+        s.run_mcmc(np.vstack(starts), 15)
+        chains.append((s.get_chain(), s.get_log_prob(), s.acceptance_fraction))
+    for c in chains[1:]:
+        for a, b in zip(chains[0], c):
+            np.testing.assert_array_equal(a, b)

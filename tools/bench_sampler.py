@@ -29,6 +29,7 @@ ap.add_argument("--spread", type=float, default=1e-3, help="sigma of the startin
 ap.add_argument("--nsources", type=int, default=1, help="fit the first NSOURCES rows of flux.dat concurrently (config 4; ncomp 1)")
 ap.add_argument("--no-native", action="store_true", help="per-half-step calls from Python instead of rb_stretch_run_dev")
 ap.add_argument("--parity-split", action="store_true", help="randomize_split=False")
+ap.add_argument("--spec", type=int, default=0, help="rb_opts.spec_half: 0 automatic, -1 never, 1 whenever the fused launch is used")
 args = ap.parse_args()
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
@@ -39,7 +40,7 @@ models = None
 if args.ncomp == 1 and args.nsources > 1:
     data = read_data(ROOT + "/data/flux.dat")
     models, starts = [], []
-    opts = _lib.default_opts(stop_rule=0 if args.stop == "pyradex" else 1, kernel=args.kernel)
+    opts = _lib.default_opts(stop_rule=0 if args.stop == "pyradex" else 1, kernel=args.kernel, spec_half=args.spec)
     for k, nm in enumerate(list(data)[:args.nsources]):
         z, lw, jup, flux, eflux = get_source(nm, data)
         tbg, ra, bounds, p0 = er1.source_setup(z)
@@ -55,7 +56,7 @@ else:
     tbg, ra, bounds, p0 = er2.source_setup(z)
     p0[3] += 0.1      # cold size > warm size so the whole starting ball has a finite prior
 ctx = _lib.Context(_lib.MolData(os.path.join(ROOT, "radex_emcee_b200", "data", "co.dat")), lr)
-opts = _lib.default_opts(stop_rule=0 if args.stop == "pyradex" else 1, kernel=args.kernel)
+opts = _lib.default_opts(stop_rule=0 if args.stop == "pyradex" else 1, kernel=args.kernel, spec_half=args.spec)
 if models is None:
     eng = CudaEngine(ctx, SLEDModel(args.ncomp, jup, flux, eflux, bounds, tbg, T_d=T_d, opts=opts))
     pos = p0 + args.spread * np.random.default_rng(20170914).standard_normal((nw, 4 * args.ncomp))
@@ -90,6 +91,6 @@ if rank == 0:
                       "ncomp": args.ncomp, "steps": args.steps, "ms_per_step": t_ms / args.steps, "solves_per_s": solves / (t_ms * 1e-3),
                       "solves_per_walker_step": solves / (nw * args.steps), "acceptance_fraction": acc, "wall_s": wall,
                       "stop": args.stop, "kernel": args.kernel, "launches": eng.launches, "nsources": args.nsources,
-                      "native_loop": s.native, "randomize_split": not args.parity_split}))
+                      "native_loop": s.native, "randomize_split": not args.parity_split, "spec_half": args.spec}))
 if world > 1:
     dist.destroy_process_group()

@@ -38,9 +38,10 @@ gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 2.7315, 2)            # warm-up
 lib.rb_debug_timing.argtypes = [C.c_void_p, C.c_int]
 lib.rb_debug_timing(None, 1)
 gpu_solve(ctx, P[:, 0], P[:, 1], P[:, 2], 2.7315, 2)
-out = (C.c_uint64 * 64)()
+out = (C.c_uint64 * 124)()
 lib.rb_debug_timing(out, 0)
-tm = np.array(out[:], dtype=np.float64).reshape(8, 8)
+tm = np.array(out[:64], dtype=np.float64).reshape(8, 8)
+tv = np.array(out[64:], dtype=np.float64).reshape(5, 12)
 names = ["load", "patch", "pivots", "backsub", "relax", "lines", "rest"]
 print("| lead levels | warp-iterations | cycles per warp-iteration | " + " | ".join(names) + " |")
 print("|---|---|---|" + "---|" * len(names))
@@ -50,3 +51,14 @@ for kp in range(3, 8):
         continue
     tot = tm[kp, :7].sum()
     print("| %d | %.3g | %.0f | " % (4 * kp, it, tot / it) + " | ".join("%.0f (%.0f %%)" % (tm[kp, i] / it, 100 * tm[kp, i] / tot) for i in range(7)) + " |")
+
+vn = ["rates", "detailed balance", "line constants", "patch", "full elimination", "full back-sub", "cached lead solve", "capture", "relax", "lines", "park/resume/top"]
+print()
+print("v2::solve by launch kind (cycles summed over warps / 1e9; share of the launch):")
+print("| launch | total Gcycles | calls | cycles per call | " + " | ".join(vn) + " |")
+print("|---|---|---|---|" + "---|" * len(vn))
+for sc, nm in ((0, "single"), (1, "A"), (2, "B"), (4, "C")):
+    tot = tv[sc, :11].sum()
+    if tot == 0:
+        continue
+    print("| %s | %.2f | %.3g | %.0f | " % (nm, tot / 1e9, tv[sc, 11], tot / max(tv[sc, 11], 1)) + " | ".join("%.1f %%" % (100 * tv[sc, i] / tot) for i in range(11)) + " |")
