@@ -274,7 +274,9 @@ def sampler_small_records(ctx, dev, stop_rule):
                     "walker_steps_per_s": 100 * len(names) * steps / (ms * 1e-3), "ms_per_step": ms / steps,
                     "solves_per_s": (s.total_solves - solves0) / (ms * 1e-3),
                     "acceptance_fraction": float(np.mean(s.acceptance_fraction)), "native_loop": bool(s.native),
-                    "loop": "rb_stretch_run_dev: CUDA graph of one step replayed"})
+                    "loop": "rb_stretch_run_dev: CUDA graph of one step replayed; second half-step proposed speculatively "
+                            "(rb_opts.spec_half = 0: one lnprob launch of 1.5 N candidates per step, same chain bit for bit; "
+                            "solves_per_s counts the speculative solves as well)"})
     return out
 
 
