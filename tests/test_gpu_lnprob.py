@@ -49,7 +49,10 @@ def test_lnprob_1comp(oracle):
     errall = np.abs(got[fin] - ref[fin])
     from test_gpu_solve import record
     record("lnprob_1comp", walkers=int(P.shape[0]), finite=int(fin.sum()), well_posed=int(ok.sum()),
-           max_abs_err_well_posed=float(err.max()), finite_within_tol=int((errall < np.maximum(ATOL, 1e-9 * np.abs(ref[fin]))).sum()))
+           max_abs_err_well_posed=float(err.max()), bar="max(1e-4 absolute, 1e-9 relative): chi^2 reaches 1e9 far from the data",
+           max_err_in_units_of_the_bar=float((err / np.maximum(ATOL, 1e-9 * np.abs(ref[ok]))).max()),
+           max_abs_err_where_abs_lnprob_below_1e4=float(err[np.abs(ref[ok]) < 1e4].max()) if (np.abs(ref[ok]) < 1e4).any() else None,
+           finite_within_tol=int((errall < np.maximum(ATOL, 1e-9 * np.abs(ref[fin]))).sum()))
     # prior short-circuit: solves only where the prior is finite (emcee_radex.py:178-180)
     assert nsolves == np.isfinite(er1.lnprior(P, bounds)).sum()
     # scalar call form
@@ -85,7 +88,9 @@ def test_lnprob_2comp(oracle):
         errall = np.abs(got[fin] - ref[fin])
         from test_gpu_solve import record
         record("lnprob_2comp_td_%s" % td, walkers=int(P.shape[0]), finite=int(fin.sum()), well_posed=int(ok.sum()),
-               max_abs_err_well_posed=float(err.max()),
+               max_abs_err_well_posed=float(err.max()), bar="max(1e-4 absolute, 1e-9 relative): chi^2 reaches 1e9 far from the data",
+               max_err_in_units_of_the_bar=float((err / np.maximum(ATOL, 1e-9 * np.abs(ref[ok]))).max()),
+               max_abs_err_where_abs_lnprob_below_1e4=float(err[np.abs(ref[ok]) < 1e4].max()) if (np.abs(ref[ok]) < 1e4).any() else None,
                finite_within_tol=int((errall < np.maximum(ATOL, 1e-9 * np.abs(ref[fin]))).sum()))
         assert nsolves == 2 * np.isfinite(er2.lnprior(P, bounds, T_d=td)).sum()
     # T_d <= 0 -> -inf everywhere

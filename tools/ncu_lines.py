@@ -67,7 +67,7 @@ src = srccache.get('lvg_v2.cuh') or (open(glob.glob('/root/repo/radex_emcee_b200
 marks = []
 for i, t in enumerate(src, 1):
     st = t.strip()
-    if st.startswith('__device__') or st.startswith('template <') and False:
+    if st.startswith('__device__') and '~' not in st and not st.startswith('__device__ unsigned long long g_t'):
         m = re.search(r'(\w+)\s*\(', st.split('__forceinline__')[-1].split('__noinline__')[-1])
         marks.append((i, m.group(1) if m else st[:30]))
     elif st.startswith('// ----') and marks and marks[-1][1].startswith('solve'):
