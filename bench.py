@@ -280,7 +280,20 @@ def sampler_small_records(ctx, dev, stop_rule):
     return out
 
 
+def emit(line):
+    """The ONE JSON line of the contract goes to the process's real stdout; everything else that libraries write to fd 1
+    while the bench runs (NCCL prints its version there) is sent to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)          # fd 1 -> stderr for the duration of the run (C libraries included)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -331,7 +344,7 @@ def main():
                                  "sample": "first %d draws of the sweep per step, %d threads; oracle/ is the bit-exact C "
                                            "restatement of the reference (its Fortran ships only as a macOS binary)" % (sample, cores)},
                 "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -573,7 +586,7 @@ def main():
                 line["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": 1, "kind": "port",
                                         "sample": "first %d draws of the same sweep, 1 thread, %.1f s; oracle/ is the "
                                                   "bit-exact C restatement of the reference" % (sample, dt)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
