@@ -975,7 +975,8 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
         const int tt = (G == 16) ? ((t == 0) ? 0 : (t == 1) ? 2 : 1) : t;
         const int l = hl + G * tt;
         lvalid[t] = l < nn;
-        ll[t] = lvalid[t] ? l : 0;
+        ll[t] = lvalid[t] ? l : ((hl < nn) ? hl : 0);   // an out-of-range lane recomputes its OWN first-trip line (and discards): it
+                                                        // reads no slot that another lane writes in this section
         const int mn = lmn[ll[t]];
         lm[t] = mn & 0xff;
         ln[t] = (mn >> 8) & 0xff;
