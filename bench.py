@@ -527,6 +527,33 @@ def main():
                                      "frac_flux_within_1e-5": float((es[fin] < 1e-5).double().mean()),
                                      "frac_pops_within_1e-5": float((ex[fin] < 1e-5).double().mean())}}
         del x2, s2, it2, st2, ex, es, sig, bright
+        # (1b) size-independent properties of the whole timed batch (this rank's n models): populations normalised and
+        # above RADEX's floor; the answer of a model does not depend on where it sits in the batch (the launches order,
+        # park and hand models between kernels by lead-block size: a permuted batch must give the same bits per model)
+        ran_ok = (d_st & 3) == 0
+        conv = d_st == 0          # stopped by the criterion (a model at the cap need not be normalised in the reference either:
+        sums = d_x.sum(dim=1)     # calls whose solution breaks down leave every level on the floor, and 0.3/0.7 of that is kept)
+        perm = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(12345))
+        keep_in = (d_tk.clone(), d_dens.clone(), d_cd.clone())
+        xp, sp_ = torch.empty_like(d_x), torch.empty_like(d_surf)
+        itp, stp = torch.empty_like(d_it), torch.empty_like(d_st)
+        d_tk.copy_(keep_in[0][perm]); d_dens.copy_(keep_in[1][perm]); d_cd.copy_(keep_in[2][perm])
+        launch(opts, sp_, xp, itp, stp)
+        torch.cuda.synchronize(dev)
+        d_tk.copy_(keep_in[0]); d_dens.copy_(keep_in[1]); d_cd.copy_(keep_in[2])
+        same_x = (xp == d_x[perm]) | (torch.isnan(xp) & torch.isnan(d_x[perm]))
+        same_s = (sp_ == d_surf[perm]) | (torch.isnan(sp_) & torch.isnan(d_surf[perm]))
+        extras["properties"] = {
+            "models": n, "what": "the timed 2^20 batch of this rank: sum of the populations, floor, and the same batch solved "
+                                 "in a random order (same bits per model wanted: the schedule must not leak into the answer)",
+            "converged_models": int(conv.sum()),
+            "max_abs_sum_xpop_minus_1_converged": float((sums[conv] - 1.0).abs().max()),
+            "models_at_the_cap_with_sum_xpop_off_by_1e-9": int((((sums - 1.0).abs() > 1e-9) & ran_ok & ~conv).sum()),
+            "min_xpop": float(d_x[ran_ok].min()),
+            "permuted_batch_models_with_identical_populations": int(same_x.all(dim=1).sum()),
+            "permuted_batch_models_with_identical_brightness": int(same_s.all(dim=1).sum()),
+            "permuted_batch_identical_niter_and_status": int(((itp == d_it[perm]) & (stp == d_st[perm])).sum())}
+        del xp, sp_, itp, stp, same_x, same_s, keep_in, perm, sums
         # (2) the sampler the north star shards over the GPUs
         extras["sampler"] = sampler_record(ctx, world, rank, dev, args.sampler_log2w, args.sampler_burn,
                                            args.sampler_steps, 0)

@@ -88,7 +88,7 @@ struct rb_ctx {
   double *bslab = nullptr;                // v2: sm_count x V2_WARPS x GSLAB doubles
   void *sched_buf = nullptr;              // v2 scheduling: parked state, keys, order (grow-only)
   size_t sched_bytes = 0;
-  unsigned long long *sched_small = nullptr;   // 64 words: histogram, offsets, cursors, parked count
+  unsigned long long *sched_small = nullptr;   // 96 words: histogram, offsets, cursors, parked count
   cudaStream_t side[6] = {};              // launch B and the five cached-engine launches run side by side (independent models)
   cudaEvent_t ev_sorted = nullptr, ev_side[6] = {};
   cudaStream_t copy_stream = nullptr;     // host entry: results of one chunk travel while the next is solved
@@ -768,7 +768,11 @@ __global__ void __launch_bounds__(V2_WARPS * 32, 1) k_lvg_solve_v2(MolDev mol, S
 
 // ---- ordering of the parked models between the two launches: counting sort by key, heaviest first ------
 constexpr int SCHED_NKEY = 16;
-// small[0..15] histogram, [16..31] bin offsets, [32..47] bin cursors, [48] number of parked models
+// small[0..15] histogram, [16..31] bin offsets, [32..47] bin cursors (from the front), [48] number of parked models,
+// [64..79] bin cursors from the back.  Within a key the models whose next call has a NaN escape probability (bit 8 of the
+// key: v2::solve, beta_nan) are placed from the front, the others from the back: those models mostly keep making calls whose
+// solution is every level on the floor, and a cached engine skips the elimination of such a call only when BOTH models of the
+// warp make one -- neighbours in the queue share a warp.
 __global__ void k_sched_hist(const int *keys, long long n, unsigned long long *small) {
   __shared__ unsigned int h[SCHED_NKEY];
   if (threadIdx.x < SCHED_NKEY) h[threadIdx.x] = 0;
@@ -791,8 +795,13 @@ __global__ void k_sched_scatter(const int *keys, long long n, unsigned long long
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n && keys[i] >= 0) {
     const int k = keys[i] & (SCHED_NKEY - 1);
-    const unsigned long long pos = atomicAdd(&small[32 + k], 1ULL);
-    order[small[16 + k] + pos] = (int)i;
+    if (keys[i] & 0x100) {
+      const unsigned long long pos = atomicAdd(&small[32 + k], 1ULL);
+      order[small[16 + k] + pos] = (int)i;
+    } else {
+      const unsigned long long pos = atomicAdd(&small[64 + k], 1ULL);
+      order[small[16 + k] + small[k] - 1ULL - pos] = (int)i;
+    }
   }
 }
 
@@ -855,6 +864,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
   constexpr int Kp = KP, n = 4 * KP, pitch = n + 2;
   int it = 0, nthick = 0, topthick = -1;
   unsigned flags = 0;   // bit t: line hl + 16 t had tau > 0.01f after the last call (RADEX's own stop rule)
+  bool beta_nan = false;   // the call about to be made has a NaN escape probability: its solution is every level on the floor (v2::solve)
   double cdmol = 1.0, cddv = 1.0;
   unsigned long long iters = 0, n_cached = 0, n_models = 0, n_inval = 0;
 #ifdef V2S_TIMING
@@ -886,17 +896,20 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
       const unsigned long long bits = reinterpret_cast<const unsigned long long *>(st)[121];
       const long long packed = reinterpret_cast<const long long *>(st)[122];
       flags = 0;
+      beta_nan = false;
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int l = hl + G * t;
         if (l < nn) {
           sm[S_TEX + l] = st[41 + l];
           sm[S_BETA + l] = st[81 + l];
+          if (st[81 + l] != st[81 + l]) beta_nan = true;
           sm[S_DNB + l] = ex[l];
           sm[S_UPB + l] = ex[v2::MAXLINE + l];
           flags |= (unsigned)((bits >> l) & 1ULL) << t;
         }
       }
+      beta_nan = __any_sync(hmask, beta_nan);
       nthick = (int)(packed & 0xffffffffLL);
       topthick = (int)(packed >> 32);
       const int nlead = n * (n + 2), nm = n * (MP - n);
@@ -911,10 +924,12 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     TM(tm1);
     // ---- one call of matrix(): radiative rates of the lead lines, lead block, M -------------------------------
     double *B = sm + S_LEAD;
+    // every model of the warp is about to make a call whose solution is NaN (v2::solve: beta_nan): no elimination
+    const bool skip_solve = __all_sync(0xffffffffu, !active || beta_nan);
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       const int l = hl + G * t;
-      if (l < nn) {
+      if (l < nn && !skip_solve) {
         const int m = lmn[l] & 0xff, nlo = (lmn[l] >> 8) & 0xff;
         if (max(m, nlo) < n) {
           const double beta = sm[S_BETA + l], a = cs[C_LA + l];
@@ -927,10 +942,10 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     __syncwarp();
     TM(tm2);
 #ifdef V2S_TIMING
-    long long tmid = 0;
-    const double tot = lead_solve<KP>(sm, hl, &tmid);
+    long long tmid = clock64();
+    const double tot = skip_solve ? __longlong_as_double(0x7ff8000000000000LL) : lead_solve<KP>(sm, hl, &tmid);
 #else
-    const double tot = lead_solve<KP>(sm, hl);
+    const double tot = skip_solve ? __longlong_as_double(0x7ff8000000000000LL) : lead_solve<KP>(sm, hl);
 #endif
     __syncwarp();
     TM(tm3);
@@ -963,6 +978,7 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
     topthick = -1;
     unsigned nflags = 0;
     double diff = 0.0, tsA = 0.0, tsB = 0.0;
+    bool nan_next = false;
     auto lines = [&](auto em) {
       constexpr unsigned EM = decltype(em)::value;   // trips whose lines get their escape probability evaluated
       int ll[NT], lm[NT], ln[NT];
@@ -1023,12 +1039,17 @@ __global__ void __launch_bounds__(v2s::Lay<KP>::WARPS * 32, 1) k_lvg_small(MolDe
           sm[S_TEX + ll[t]] = 0.5 * (thistex + ltold[t]);
           // a trip without lead lines keeps beta = 1 (its lines are frozen; if one turns thick the model leaves this engine
           // and the leave path below evaluates escprob for it)
-          if ((EM >> tt) & 1u) sm[S_BETA + ll[t]] = (fabs(ltaur[t]) < v2::KC[v2::KC_F001]) ? 1.0 : lmid[t];
+          if ((EM >> tt) & 1u) {
+            const double beta_next = (fabs(ltaur[t]) < v2::KC[v2::KC_F001]) ? 1.0 : lmid[t];
+            sm[S_BETA + ll[t]] = beta_next;
+            if (beta_next != beta_next) nan_next = true;
+          }
         }
       }
     };
     if (lead_fast) lines(std::integral_constant<unsigned, LEAD_FAST>()); else lines(std::integral_constant<unsigned, LEAD_ALL>());
     flags = nflags;
+    beta_nan = __any_sync(hmask, nan_next);
     topthick = group_max_int(hmask, topthick);
     bool stop;
     if (cfg.stop_rule == RB_STOP_RADEX) {
@@ -1700,7 +1721,7 @@ static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg_in, SolveIO io
     CUDA_TRY(cudaMalloc(&ctx->sched_buf, b_all));
     ctx->sched_bytes = b_all;
   }
-  if (!ctx->sched_small) CUDA_TRY(cudaMalloc(&ctx->sched_small, 64 * sizeof(unsigned long long)));
+  if (!ctx->sched_small) CUDA_TRY(cudaMalloc(&ctx->sched_small, 96 * sizeof(unsigned long long)));
   char *base = static_cast<char *>(ctx->sched_buf);
   io.state = reinterpret_cast<double *>(base);
   io.keys = reinterpret_cast<int *>(base + b_state);
@@ -1712,7 +1733,7 @@ static int launch_solve_pipeline(rb_ctx *ctx, const SolveCfg &cfg_in, SolveIO io
     io.ext = reinterpret_cast<double *>(base + b_state + 3 * b_int + b_off);
     io.ext_cap = ext_cap;
   }
-  CUDA_TRY(cudaMemsetAsync(ctx->sched_small, 0, 64 * sizeof(unsigned long long), ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->sched_small, 0, 96 * sizeof(unsigned long long), ctx->stream));
   io.sched = 1;
   k_lvg_solve_v2<<<L.blocks, L.warps_per_block * 32, L.smem, ctx->stream>>>(ctx->mol, cfg, io);
   const int tpb = 256, nb = (int)((n + tpb - 1) / tpb);
