@@ -36,6 +36,14 @@ def test_round2_line_carries_parity_sampler_and_stop_rule_records():
         assert r["value"] > d["value"] and r["iters_per_solve"] < d["iters_per_solve"]
         assert len(r["error_vs_fixed_point"]["flux_rel_err"]) == 5
         assert d["roofline"]["traffic"] is None or d["roofline"]["traffic"] > d["e2e"]["d2h_bytes_per_step"]
+        # size-independent properties of the whole timed 2^20 batch: converged models normalised, and the same batch in a
+        # random order gives the same bits for every model (nothing of the launch schedule leaks into an answer)
+        q = d["properties"]
+        assert q["models"] == 1 << 20 and q["converged_models"] > 0.85 * q["models"]
+        assert q["max_abs_sum_xpop_minus_1_converged"] < 1e-11 and q["min_xpop"] >= 1e-20
+        for k in ("permuted_batch_models_with_identical_populations", "permuted_batch_models_with_identical_brightness",
+                  "permuted_batch_identical_niter_and_status"):
+            assert q[k] == q["models"], k
 
 
 def test_own_arm_line():
